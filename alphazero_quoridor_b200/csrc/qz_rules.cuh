@@ -1,0 +1,537 @@
+// qz_rules.cuh -- Quoridor rules on bitboards, shared by every kernel in this directory.
+//
+// Everything here is `__host__ __device__` so the exact code the sm_100a kernels run can also be
+// compiled for the host by tests/host_harness (a TEST build, never shipped or loaded by the product)
+// and diffed against the oracle in a container without a GPU.
+//
+// Data model (DESIGN.md "Data layout"):
+//   QzState  24 B/game: u64 H (horizontal walls, bit ix = r*8+c), u64 V (vertical walls), u64 meta
+//            meta: byte0 P1 tile (int8, may be 81..89 after an off-board winning jump), byte1 P2 tile
+//            (int8, may be -9..-1), byte2/3 walls left P1/P2, byte4 mover (1|2), byte5 flags, bytes6-7 ply
+//   BB       81-bit tile set, tile t = r*9+c at bit t, as 3 x u32 (bits 81..95 always zero)
+//   legal mask 140 bits as 3 x u64: bit a = action a (0..11 pawn, 12..75 H wall ix a-12, 76..139 V wall ix a-76)
+//
+// Reference semantics restated (file:line are into the reference repository):
+//   corner values        quoridor.py:356-418  (incl. the row-0 NE/NW aliasing at :388,:392)
+//   pawn moves           quoridor.py:272-353
+//   wall prechecks       quoridor.py:432-461
+//   path check           quoridor.py:463-528  (BFS -> bit-parallel flood fill; same reachability)
+//   step / winner        quoridor.py:159-202, :217-269
+//   state planes         quoridor.py:58-131
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define QZ_HD __host__ __device__ __forceinline__
+#else
+#define QZ_HD static inline
+#endif
+
+struct QzState {
+    uint64_t H, V, meta;
+};
+
+// ---- meta accessors -------------------------------------------------------------------------
+#define QZ_FLAG_DONE 0x01u
+#define QZ_FLAG_WINNER_SHIFT 1      // bits 1-2: winner (0 none, 1, 2)
+#define QZ_FLAG_STALEMATE 0x08u     // mover has no legal action (reference: actions()==[] then crashes)
+#define QZ_FLAG_TRUNCATED 0x10u     // ply cap hit (engine-side cap; reference loops forever)
+#define QZ_FLAG_ILLEGAL 0x20u       // safe-mode step rejected the action (quoridor.py:167-169)
+
+QZ_HD int qz_p1(uint64_t m) { return (int)(int8_t)(m & 0xFF); }
+QZ_HD int qz_p2(uint64_t m) { return (int)(int8_t)((m >> 8) & 0xFF); }
+QZ_HD int qz_w1(uint64_t m) { return (int)((m >> 16) & 0xFF); }
+QZ_HD int qz_w2(uint64_t m) { return (int)((m >> 24) & 0xFF); }
+QZ_HD int qz_cur(uint64_t m) { return (int)((m >> 32) & 0xFF); }
+QZ_HD unsigned qz_flags(uint64_t m) { return (unsigned)((m >> 40) & 0xFF); }
+QZ_HD unsigned qz_ply(uint64_t m) { return (unsigned)((m >> 48) & 0xFFFF); }
+QZ_HD bool qz_done(uint64_t m) { return (m >> 40) & QZ_FLAG_DONE; }
+QZ_HD int qz_winner(uint64_t m) { return (int)((m >> (40 + QZ_FLAG_WINNER_SHIFT)) & 3); }
+
+QZ_HD uint64_t qz_pack_meta(int p1, int p2, int w1, int w2, int cur, unsigned flags, unsigned ply) {
+    return (uint64_t)(uint8_t)p1 | ((uint64_t)(uint8_t)p2 << 8) | ((uint64_t)(w1 & 0xFF) << 16) |
+           ((uint64_t)(w2 & 0xFF) << 24) | ((uint64_t)(cur & 0xFF) << 32) | ((uint64_t)(flags & 0xFF) << 40) |
+           ((uint64_t)(ply & 0xFFFF) << 48);
+}
+
+// quoridor.py:26-56
+QZ_HD QzState qz_initial_state() {
+    QzState s;
+    s.H = 0; s.V = 0;
+    s.meta = qz_pack_meta(4, 76, 10, 10, 1, 0, 0);
+    return s;
+}
+
+// ---- small portable intrinsics ------------------------------------------------------------------
+QZ_HD int qz_popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+QZ_HD int qz_popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+QZ_HD uint32_t qz_fshl(uint32_t lo, uint32_t hi, int k) {   // high word of ((hi:lo) << k), 0<k<32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, k);
+#else
+    return (hi << k) | (lo >> (32 - k));
+#endif
+}
+QZ_HD uint32_t qz_fshr(uint32_t lo, uint32_t hi, int k) {   // low word of ((hi:lo) >> k), 0<k<32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, k);
+#else
+    return (lo >> k) | (hi << (32 - k));
+#endif
+}
+// index of the k-th (0-based) set bit of m; m must have more than k bits set
+QZ_HD int qz_nth_bit64(uint64_t m, int k) {
+#if defined(__CUDA_ARCH__)
+    uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+    int cl = __popc(lo);
+    uint32_t w = lo; int base = 0;
+    if (k >= cl) { k -= cl; w = hi; base = 32; }
+    return base + (int)__fns(w, 0, k + 1);
+#else
+    for (int i = 0; i < k; i++) m &= m - 1;
+    return __builtin_ctzll(m);
+#endif
+}
+
+// ---- 81-bit boards --------------------------------------------------------------------------------
+struct BB {
+    uint32_t w0, w1, w2;
+};
+QZ_HD BB bb_zero() { BB b; b.w0 = b.w1 = b.w2 = 0; return b; }
+QZ_HD BB bb_bit(int t) {   // 0 <= t <= 80
+    BB b;
+    b.w0 = t < 32 ? 1u << t : 0u;
+    b.w1 = (t >= 32 && t < 64) ? 1u << (t - 32) : 0u;
+    b.w2 = t >= 64 ? 1u << (t - 64) : 0u;
+    return b;
+}
+QZ_HD bool bb_test(BB b, int t) {
+    uint32_t w = t < 32 ? b.w0 : (t < 64 ? b.w1 : b.w2);
+    return (w >> (t & 31)) & 1u;
+}
+QZ_HD BB bb_and(BB a, BB b) { BB r; r.w0 = a.w0 & b.w0; r.w1 = a.w1 & b.w1; r.w2 = a.w2 & b.w2; return r; }
+QZ_HD BB bb_or(BB a, BB b) { BB r; r.w0 = a.w0 | b.w0; r.w1 = a.w1 | b.w1; r.w2 = a.w2 | b.w2; return r; }
+QZ_HD BB bb_andn(BB a, BB b) { BB r; r.w0 = a.w0 & ~b.w0; r.w1 = a.w1 & ~b.w1; r.w2 = a.w2 & ~b.w2; return r; }
+QZ_HD bool bb_eq(BB a, BB b) { return ((a.w0 ^ b.w0) | (a.w1 ^ b.w1) | (a.w2 ^ b.w2)) == 0; }
+QZ_HD bool bb_any(BB a) { return (a.w0 | a.w1 | a.w2) != 0; }
+QZ_HD BB bb_shl(BB a, int k) {   // toward higher tiles; caller guarantees nothing leaves bit 80
+    BB r;
+    r.w2 = qz_fshl(a.w1, a.w2, k);
+    r.w1 = qz_fshl(a.w0, a.w1, k);
+    r.w0 = a.w0 << k;
+    return r;
+}
+QZ_HD BB bb_shr(BB a, int k) {
+    BB r;
+    r.w0 = qz_fshr(a.w0, a.w1, k);
+    r.w1 = qz_fshr(a.w1, a.w2, k);
+    r.w2 = a.w2 >> k;
+    return r;
+}
+
+#define QZ_ROW0_W0 0x1FFu          // tiles 0..8
+#define QZ_ROW8_W2 0x1FF00u        // tiles 72..80 = bits 8..16 of w2
+#define QZ_BOARD_W2 0x1FFFFu       // tiles 64..80
+
+// 8x8 intersection mask (bit r*8+c) -> 9-stride board (bit r*9+c); column 8 and row 8 stay empty
+QZ_HD BB bb_spread8(uint64_t x) {
+    // rows 4..7 up by 4, then rows {2,3,6,7} by 2, then odd rows by 1 (each row r moves up by r)
+    uint32_t lo = (uint32_t)x, hi = (uint32_t)(x >> 32);
+    // after step 1: bits 0..31 = rows 0-3, bits 36..67 = rows 4-7  -> 3 words
+    uint32_t a0 = lo, a1 = hi << 4, a2 = hi >> 28;
+    // step 2: rows {2,3} are bits 16..31 of a0; rows {6,7} are bits 52..67 (a1 bits 20..31, a2 bits 0..3)
+    uint32_t m0 = a0 & 0xFFFF0000u, m1 = a1 & 0xFFF00000u, m2 = a2;
+    uint32_t k0 = a0 & 0x0000FFFFu, k1 = a1 & 0x000FFFFFu;
+    uint32_t b0 = k0 | (m0 << 2);
+    uint32_t b1 = k1 | (m0 >> 30) | (m1 << 2);
+    uint32_t b2 = (m1 >> 30) | (m2 << 2);
+    // now row r sits at bit 8r + 2*(r>>1) + 4*(r>>2)... explicitly: r0@0 r1@8 r2@18 r3@26 r4@36 r5@44 r6@54 r7@62
+    // step 3: odd rows up by 1: r1@8..15 (b0), r3@26..33 (b0 bits 26-31, b1 bits 0-1), r5@44..51 (b1 12..19),
+    //         r7@62..69 (b1 bits 30-31, b2 bits 0-5)
+    uint32_t o0 = b0 & 0xFC00FF00u, o1 = b1 & 0xC00FF003u, o2 = b2 & 0x3Fu;
+    uint32_t e0 = b0 & ~0xFC00FF00u, e1 = b1 & ~0xC00FF003u, e2 = b2 & ~0x3Fu;
+    BB r;
+    r.w0 = e0 | (o0 << 1);
+    r.w1 = e1 | (o0 >> 31) | (o1 << 1);
+    r.w2 = e2 | (o1 >> 31) | (o2 << 1);
+    return r;
+}
+
+// ---- direction masks ("a pawn on tile t may make the plain move X"), opponent ignored ----------------
+// SURVEY.md Appendix A table, derived from quoridor.py:287-293 + :356-418; note the row-0 quirk
+// (N and E from row 0 test the wall WEST of the tile's NE corner).
+struct QzDirs {
+    BB n, s, e, w;
+};
+
+#define QZ_COL0_W0 0x08040201u     // tiles 0,9,18,27
+#define QZ_COL0_W1 0x80402010u     // tiles 36,45,54,63
+#define QZ_COL0_W2 0x00000100u     // tile 72
+#define QZ_COL8_W0 0x04020100u     // tiles 8,17,26
+#define QZ_COL8_W1 0x40201008u     // tiles 35,44,53,62
+#define QZ_COL8_W2 0x00010080u     // tiles 71,80
+
+QZ_HD QzDirs qz_dirs(uint64_t H, uint64_t V) {
+    BB h9 = bb_spread8(H), v9 = bb_spread8(V);
+    BB hh = bb_or(h9, bb_shl(h9, 1));            // h(r,c) | h(r,c-1) at tile (r,c)
+    BB vv = bb_or(v9, bb_shl(v9, 9));            // v(r,c) | v(r-1,c) at tile (r,c)
+    // blocked-N: regular rows use hh; row 0 uses h(0,c-1) (c>0) or h(0,0) (c==0); row 8 never moves N
+    uint32_t r0h = h9.w0 & 0xFFu;                // row-0 H walls, columns 0..7
+    uint32_t r0v = v9.w0 & 0xFFu;
+    BB bn = hh;
+    bn.w0 = (bn.w0 & ~QZ_ROW0_W0) | ((r0h << 1) | (r0h & 1u));
+    bn.w2 |= QZ_ROW8_W2;
+    // blocked-S: h(r-1,c) | h(r-1,c-1); row 0 never moves S
+    BB bs = bb_shl(hh, 9);
+    bs.w0 |= QZ_ROW0_W0;
+    // blocked-E: v(r,c) | v(r-1,c); row 0: v(0,c-1) (c>0) or v(0,0); column 8 never
+    BB be = vv;
+    be.w0 = (be.w0 & ~QZ_ROW0_W0) | ((r0v << 1) | (r0v & 1u));
+    be.w0 |= QZ_COL8_W0; be.w1 |= QZ_COL8_W1; be.w2 |= QZ_COL8_W2;
+    // blocked-W: v(r,c-1) | v(r-1,c-1); column 0 never
+    BB bw = bb_shl(vv, 1);
+    bw.w0 |= QZ_COL0_W0; bw.w1 |= QZ_COL0_W1; bw.w2 |= QZ_COL0_W2;
+    QzDirs d;
+    d.n.w0 = ~bn.w0; d.n.w1 = ~bn.w1; d.n.w2 = ~bn.w2 & QZ_BOARD_W2;
+    d.s.w0 = ~bs.w0; d.s.w1 = ~bs.w1; d.s.w2 = ~bs.w2 & QZ_BOARD_W2;
+    d.e.w0 = ~be.w0; d.e.w1 = ~be.w1; d.e.w2 = ~be.w2 & QZ_BOARD_W2;
+    d.w.w0 = ~bw.w0; d.w.w1 = ~bw.w1; d.w.w2 = ~bw.w2 & QZ_BOARD_W2;
+    return d;
+}
+
+// Tiles whose N / S (horizontal wall) or E / W (vertical wall) move a single new wall at
+// intersection ix removes.  The blocked sets are unions over walls, so placing a candidate is
+// `dirs.x &= ~delta` -- no re-spread per candidate.
+QZ_HD void qz_dirs_place_h(QzDirs &d, int ix) {
+    int r = ix >> 3, c = ix & 7, t = r * 9 + c;
+    BB dn;
+    if (r == 0) { dn = bb_bit(t + 1); if (c == 0) dn.w0 |= 1u; }
+    else dn = bb_or(bb_bit(t), bb_bit(t + 1));
+    BB ds = bb_or(bb_bit(t + 9), bb_bit(t + 10));
+    d.n = bb_andn(d.n, dn);
+    d.s = bb_andn(d.s, ds);
+}
+QZ_HD void qz_dirs_place_v(QzDirs &d, int ix) {
+    int r = ix >> 3, c = ix & 7, t = r * 9 + c;
+    BB de;
+    if (r == 0) { de = bb_or(bb_bit(t + 1), bb_bit(t + 9)); if (c == 0) de.w0 |= 1u; }
+    else de = bb_or(bb_bit(t), bb_bit(t + 9));
+    BB dw = bb_or(bb_bit(t + 1), bb_bit(t + 10));
+    d.e = bb_andn(d.e, de);
+    d.w = bb_andn(d.w, dw);
+}
+
+// ---- corner values (quoridor.py:356-418): 0 none, 1 horizontal, 2 vertical -----------------------------
+#define QZ_CH 1
+#define QZ_CV 2
+QZ_HD int qz_wall_at(uint64_t H, uint64_t V, int r, int c) {
+    int i = r * 8 + c;
+    return (int)((H >> i) & 1u) | ((int)((V >> i) & 1u) << 1);
+}
+struct QzCorners {
+    int nw, ne, se, sw;
+};
+QZ_HD QzCorners qz_corners(uint64_t H, uint64_t V, int t) {   // 0 <= t <= 80
+    int r = t / 9, c = t - 9 * r;
+    QzCorners k;
+    if (r == 8) {
+        k.ne = QZ_CH;
+        k.nw = (c == 0) ? QZ_CV : QZ_CH;
+        k.se = (c == 8) ? QZ_CV : qz_wall_at(H, V, 7, c);
+        k.sw = (c == 0) ? QZ_CV : qz_wall_at(H, V, 7, c - 1);
+    } else if (r == 0) {
+        k.sw = QZ_CH;
+        k.se = (c == 8) ? QZ_CV : QZ_CH;
+        if (c == 0) { k.nw = QZ_CV; k.ne = qz_wall_at(H, V, 0, 0); }
+        else { k.nw = k.ne = qz_wall_at(H, V, 0, c - 1); }          // the :388/:392 aliasing
+    } else {
+        k.nw = (c == 0) ? QZ_CV : qz_wall_at(H, V, r, c - 1);
+        k.sw = (c == 0) ? QZ_CV : qz_wall_at(H, V, r - 1, c - 1);
+        k.ne = (c == 8) ? QZ_CV : qz_wall_at(H, V, r, c);
+        k.se = (c == 8) ? QZ_CV : qz_wall_at(H, V, r - 1, c);
+    }
+    return k;
+}
+
+// quoridor.py:272-353 -> 12-bit mask, bit id = action id (0 N,1 S,2 E,3 W,4 NN,5 SS,6 EE,7 WW,8 NE,9 NW,10 SE,11 SW)
+// L must be on the board; O is the opponent's tile (on the board for every non-terminal state).
+QZ_HD uint32_t qz_pawn_moves(uint64_t H, uint64_t V, int L, int O, int player) {
+    QzCorners I = qz_corners(H, V, L);
+    int row = L / 9;
+    bool on = (L == O - 9), os = (L == O + 9), oe = (L == O - 1), ow = (L == O + 1);
+    uint32_t m = 0;
+    bool n = I.nw != QZ_CH && I.ne != QZ_CH && !on;
+    bool s = I.sw != QZ_CH && I.se != QZ_CH && !os;
+    bool e = I.ne != QZ_CV && I.se != QZ_CV && !oe;
+    bool w = I.nw != QZ_CV && I.sw != QZ_CV && !ow;
+    if (n || (player == 1 && row == 8)) m |= 1u << 0;
+    if (s || (player == 2 && row == 0)) m |= 1u << 1;
+    if (e) m |= 1u << 2;
+    if (w) m |= 1u << 3;
+    if (!(on || os || oe || ow) || O < 0 || O > 80) return m;
+    QzCorners P = qz_corners(H, V, O);
+    if (on && I.ne != QZ_CH && I.nw != QZ_CH) {
+        if ((P.nw != QZ_CH && P.ne != QZ_CH) || (row == 7 && player == 1)) m |= 1u << 4;
+        if (P.ne != QZ_CV && I.ne != QZ_CV) m |= 1u << 8;
+        if (P.nw != QZ_CV && I.nw != QZ_CV) m |= 1u << 9;
+    } else if (os && I.se != QZ_CH && I.sw != QZ_CH) {
+        if ((P.sw != QZ_CH && P.se != QZ_CH) || (row == 1 && player == 2)) m |= 1u << 5;
+        if (P.se != QZ_CV && I.se != QZ_CV) m |= 1u << 10;
+        if (P.sw != QZ_CV && I.sw != QZ_CV) m |= 1u << 11;
+    } else if (oe && I.se != QZ_CV && I.ne != QZ_CV) {
+        if (P.se != QZ_CV && P.ne != QZ_CV) m |= 1u << 6;
+        if (P.ne != QZ_CH) m |= 1u << 8;
+        if (P.se != QZ_CH) m |= 1u << 10;
+    } else if (ow && I.sw != QZ_CV && I.nw != QZ_CV) {
+        if (P.nw != QZ_CV && P.sw != QZ_CV) m |= 1u << 7;
+        if (P.nw != QZ_CH) m |= 1u << 9;
+        if (P.sw != QZ_CH) m |= 1u << 11;
+    }
+    return m;
+}
+
+// tile offset of each pawn action (quoridor.py:217-243)
+QZ_HD int qz_delta(int a) {
+    // {9,-9,1,-1,18,-18,2,-2,10,8,-8,-10} packed as bytes to stay in registers
+    const uint64_t lo = 0xFE02EE12FF01F709ull;   // a = 0..7 : 9,-9,1,-1,18,-18,2,-2
+    const uint32_t hi = 0xF6F8080Au;             // a = 8..11: 10,8,-8,-10
+    return a < 8 ? (int)(int8_t)(lo >> (8 * a)) : (int)(int8_t)(hi >> (8 * (a - 8)));
+}
+
+// ---- jump edges seen by the path check ------------------------------------------------------------------
+// In _bfs_to_goal (quoridor.py:479-528) the opponent pawn is a fixed obstacle: plain moves into its
+// tile are dropped and up to three jump edges leave each of the four neighbouring tiles.  Encoded as one
+// u32: byte i = actions 4..11 available from source tile O + QZ_SRC[i]  (i: 0 = O-9, 1 = O+9, 2 = O-1, 3 = O+1).
+QZ_HD int qz_jump_src(int O, int i) { return O + (i == 0 ? -9 : (i == 1 ? 9 : (i == 2 ? -1 : 1))); }
+
+QZ_HD uint32_t qz_jump_set(uint64_t H, uint64_t V, int O, int player) {
+    uint32_t js = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int src = qz_jump_src(O, i);
+        if (src < 0 || src > 80) continue;
+        uint32_t m = qz_pawn_moves(H, V, src, O, player) >> 4;
+        js |= (m & 0xFFu) << (8 * i);
+    }
+    return js;
+}
+
+// intersections whose content can change qz_jump_set(.., O, ..): rows r-2..r+1, cols c-2..c+1 of O=(r,c)
+QZ_HD uint64_t qz_jump_near_mask(int O) {
+    int r = O / 9, c = O - 9 * r;
+    int r0 = r - 2 < 0 ? 0 : r - 2, r1 = r + 1 > 7 ? 7 : r + 1;
+    int c0 = c - 2 < 0 ? 0 : c - 2, c1 = c + 1 > 7 ? 7 : c + 1;
+    uint64_t rowbits = ((1ull << (c1 - c0 + 1)) - 1) << c0;
+    uint64_t m = 0;
+    for (int rr = r0; rr <= r1; rr++) m |= rowbits << (8 * rr);
+    return m;
+}
+
+// ---- the path check: can `player` standing on `start` still reach its goal row? -------------------------
+// Same reachability as quoridor.py:479-528: closure of {plain moves not entering O} U {jump edges};
+// touching the goal row ends the search; off-board landings (NN from row 7 / SS from row 1) are recorded by
+// the reference but never expanded and never equal the goal row, so they are dropped here.
+QZ_HD bool qz_reaches_goal(const QzDirs &d, int start, int O, uint32_t jumps, int player) {
+    BB reach = bb_bit(start);
+    BB keep = bb_bit(O);
+    keep.w0 = ~keep.w0; keep.w1 = ~keep.w1; keep.w2 = ~keep.w2;
+    for (;;) {
+        for (;;) {
+            BB a = bb_shl(bb_and(reach, d.n), 9);
+            BB b = bb_shr(bb_and(reach, d.s), 9);
+            BB c = bb_shl(bb_and(reach, d.e), 1);
+            BB e = bb_shr(bb_and(reach, d.w), 1);
+            BB nxt;
+            nxt.w0 = (reach.w0 | ((a.w0 | b.w0 | c.w0 | e.w0) & keep.w0));
+            nxt.w1 = (reach.w1 | ((a.w1 | b.w1 | c.w1 | e.w1) & keep.w1));
+            nxt.w2 = (reach.w2 | ((a.w2 | b.w2 | c.w2 | e.w2) & keep.w2));
+            if (player == 1 ? (nxt.w2 & QZ_ROW8_W2) : (nxt.w0 & QZ_ROW0_W0)) return true;
+            if (bb_eq(nxt, reach)) break;
+            reach = nxt;
+        }
+        if (jumps == 0) return false;
+        BB add = bb_zero();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            uint32_t byte = (jumps >> (8 * i)) & 0xFFu;
+            if (byte == 0) continue;
+            int src = qz_jump_src(O, i);
+            if (!bb_test(reach, src)) continue;
+            for (int b = 0; b < 8; b++) {
+                if (!((byte >> b) & 1u)) continue;
+                int land = src + qz_delta(4 + b);
+                if (land >= 0 && land <= 80) add = bb_or(add, bb_bit(land));
+            }
+        }
+        if (player == 1 ? (add.w2 & QZ_ROW8_W2) : (add.w0 & QZ_ROW0_W0)) return true;
+        BB nxt = bb_or(reach, add);
+        if (bb_eq(nxt, reach)) return false;
+        reach = nxt;
+    }
+}
+
+// ---- wall candidates ------------------------------------------------------------------------------------
+// quoridor.py:432-461 without the path check: the empty intersections where an H (resp. V) wall does not
+// overlap a collinear neighbour.
+QZ_HD uint64_t qz_hcand(uint64_t H, uint64_t V) {
+    const uint64_t COL0 = 0x0101010101010101ull, COL7 = 0x8080808080808080ull;
+    return ~(H | V) & ~((H << 1) & ~COL0) & ~((H >> 1) & ~COL7);
+}
+QZ_HD uint64_t qz_vcand(uint64_t H, uint64_t V) { return ~(H | V) & ~(V << 8) & ~(V >> 8); }
+
+// Everything one position's 128-candidate sweep shares (registers of every lane of the warp).
+struct QzSweep {
+    uint64_t H, V;
+    QzDirs dirs;
+    int p1, p2;
+    uint32_t j1, j2;        // jump sets seen by P1's search (obstacle P2) and P2's search (obstacle P1)
+    uint64_t near1, near2;  // intersections that can change j1 / j2
+};
+
+QZ_HD QzSweep qz_sweep_prepare(uint64_t H, uint64_t V, int p1, int p2) {
+    QzSweep w;
+    w.H = H; w.V = V; w.p1 = p1; w.p2 = p2;
+    w.dirs = qz_dirs(H, V);
+    w.j1 = qz_jump_set(H, V, p2, 1);
+    w.j2 = qz_jump_set(H, V, p1, 2);
+    w.near1 = qz_jump_near_mask(p2);
+    w.near2 = qz_jump_near_mask(p1);
+    return w;
+}
+
+// quoridor.py:463-477 (_blocks_path negated): true iff placing the wall leaves both players a path.
+QZ_HD bool qz_wall_keeps_paths(const QzSweep &w, int ix, bool vertical) {
+    QzDirs d = w.dirs;
+    uint64_t H = w.H, V = w.V;
+    uint64_t bit = 1ull << ix;
+    if (vertical) { qz_dirs_place_v(d, ix); V |= bit; }
+    else { qz_dirs_place_h(d, ix); H |= bit; }
+    uint32_t j1 = (w.near1 & bit) ? qz_jump_set(H, V, w.p2, 1) : w.j1;
+    if (!qz_reaches_goal(d, w.p1, w.p2, j1, 1)) return false;
+    uint32_t j2 = (w.near2 & bit) ? qz_jump_set(H, V, w.p1, 2) : w.j2;
+    return qz_reaches_goal(d, w.p2, w.p1, j2, 2);
+}
+
+// ---- step (quoridor.py:159-186, :193-202, :217-269) ---------------------------------------------------------
+// Applies `action` for the mover WITHOUT checking legality (the reference's safe=False behaviour); a
+// finished game is left untouched.  Returns the new state.
+QZ_HD QzState qz_apply(QzState s, int action) {
+    uint64_t m = s.meta;
+    if (qz_done(m)) return s;
+    int p1 = qz_p1(m), p2 = qz_p2(m), w1 = qz_w1(m), w2 = qz_w2(m), cur = qz_cur(m);
+    unsigned flags = qz_flags(m), ply = qz_ply(m);
+    if (action < 12) {
+        int dlt = qz_delta(action);
+        if (cur == 1) p1 += dlt; else p2 += dlt;
+    } else {
+        int a = action - 12;
+        if (a < 64) s.H |= 1ull << a; else s.V |= 1ull << (a - 64);
+        if (cur == 1) w1 -= 1; else w2 -= 1;
+    }
+    int winner = p2 < 9 ? 2 : (p1 > 71 ? 1 : 0);       // P2 tested first (:196-201)
+    if (winner) flags |= QZ_FLAG_DONE | ((unsigned)winner << QZ_FLAG_WINNER_SHIFT);
+    else cur = 3 - cur;                                  // mover is NOT rotated on a winning move (:176-181)
+    ply = ply < 0xFFFFu ? ply + 1 : ply;
+    s.meta = qz_pack_meta(p1, p2, w1, w2, cur, flags, ply);
+    return s;
+}
+
+// true iff both pawns stand on the board (every non-terminal state; terminal ones may not)
+QZ_HD bool qz_on_board(uint64_t m) {
+    int p1 = qz_p1(m), p2 = qz_p2(m);
+    return p1 >= 0 && p1 <= 80 && p2 >= 0 && p2 <= 80;
+}
+
+// pawn part of actions() for the mover (quoridor.py:146)
+QZ_HD uint32_t qz_mover_pawn_moves(const QzState &s) {
+    int cur = qz_cur(s.meta);
+    int L = cur == 1 ? qz_p1(s.meta) : qz_p2(s.meta);
+    int O = cur == 1 ? qz_p2(s.meta) : qz_p1(s.meta);
+    return qz_pawn_moves(s.H, s.V, L, O, cur);
+}
+QZ_HD int qz_mover_walls(uint64_t m) { return qz_cur(m) == 1 ? qz_w1(m) : qz_w2(m); }
+
+// 140-bit mask assembly: pawn (12 bits) | Hlegal << 12 | Vlegal << 76
+QZ_HD void qz_pack_mask(uint32_t pawn, uint64_t hl, uint64_t vl, uint64_t out[3]) {
+    out[0] = (uint64_t)pawn | (hl << 12);
+    out[1] = (hl >> 52) | (vl << 12);
+    out[2] = vl >> 52;
+}
+
+// Sequential full sweep (one thread).  The warp kernel in qz_env.cu distributes the same
+// qz_wall_keeps_paths calls over 32 lanes; this form serves single-thread users and the host harness.
+QZ_HD void qz_legal_mask_seq(const QzState &s, uint64_t out[3]) {
+    out[0] = out[1] = out[2] = 0;
+    if (qz_done(s.meta) || !qz_on_board(s.meta)) return;
+    uint32_t pawn = qz_mover_pawn_moves(s);
+    uint64_t hl = 0, vl = 0;
+    if (qz_mover_walls(s.meta) > 0) {
+        QzSweep w = qz_sweep_prepare(s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
+        uint64_t hc = qz_hcand(s.H, s.V), vc = qz_vcand(s.H, s.V);
+        for (int ix = 0; ix < 64; ix++) {
+            if (((hc >> ix) & 1) && qz_wall_keeps_paths(w, ix, false)) hl |= 1ull << ix;
+            if (((vc >> ix) & 1) && qz_wall_keeps_paths(w, ix, true)) vl |= 1ull << ix;
+        }
+    }
+    qz_pack_mask(pawn, hl, vl, out);
+}
+
+// Position of action `a` in the reference's actions() ordering given the legal mask parts:
+// pawn ids ascending, then H(ix0),V(ix0),H(ix1),V(ix1),... (quoridor.py:157,420-430)
+QZ_HD int qz_action_rank(uint32_t pawn, uint64_t hl, uint64_t vl, int a) {
+    if (a < 12) return qz_popc32(pawn & ((1u << a) - 1u));
+    int np = qz_popc32(pawn);
+    if (a < 76) {
+        int ix = a - 12;
+        uint64_t below = (1ull << ix) - 1ull;
+        return np + qz_popc64(hl & below) + qz_popc64(vl & below);
+    }
+    int ix = a - 76;
+    uint64_t below = (1ull << ix) - 1ull;
+    return np + qz_popc64(hl & below) + qz_popc64(vl & below) + (int)((hl >> ix) & 1ull);
+}
+QZ_HD void qz_unpack_mask(const uint64_t m[3], uint32_t &pawn, uint64_t &hl, uint64_t &vl) {
+    pawn = (uint32_t)(m[0] & 0xFFFu);
+    hl = (m[0] >> 12) | (m[1] << 52);
+    vl = (m[1] >> 12) | (m[2] << 52);
+}
+
+// ---- state planes (quoridor.py:58-131): value of plane p at cell (r,c), as 0/1 -----------------------------
+// planes: 0 no-wall, 1 vertical, 2 horizontal (8x8 padded to 9x9 at the bottom/right), 3 mover pawn,
+// 4 opponent pawn, 5-14 mover walls-left one-hot at index w-1 (w=0 -> index 9), 15-24 opponent, 25 mover==P2.
+// Off-board pawn tiles follow numpy's negative wrap for -81..-1; tiles > 80 (reference: IndexError) light nothing.
+QZ_HD int qz_plane_value(const QzState &s, int p, int r, int c) {
+    uint64_t m = s.meta;
+    int cur = qz_cur(m);
+    if (p <= 2) {
+        if (r > 7 || c > 7) return 0;
+        int i = r * 8 + c;
+        int h = (int)((s.H >> i) & 1u), v = (int)((s.V >> i) & 1u);
+        return p == 0 ? (1 - (h | v)) : (p == 1 ? v : h);
+    }
+    if (p <= 4) {
+        int mine = cur == 1 ? qz_p1(m) : qz_p2(m), theirs = cur == 1 ? qz_p2(m) : qz_p1(m);
+        int t = p == 3 ? mine : theirs;
+        if (t < 0) t += 81;
+        return t == r * 9 + c;
+    }
+    if (p <= 24) {
+        int wm = cur == 1 ? qz_w1(m) : qz_w2(m), wo = cur == 1 ? qz_w2(m) : qz_w1(m);
+        int w = p <= 14 ? wm : wo;
+        int idx = w - 1 < 0 ? 9 : w - 1;
+        return (p - (p <= 14 ? 5 : 15)) == idx;
+    }
+    return cur == 2;
+}

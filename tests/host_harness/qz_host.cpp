@@ -1,0 +1,61 @@
+// TEST BUILD ONLY.  Compiles the product's __host__ __device__ rules header (the exact code the sm_100a
+// kernels run) for the host so it can be diffed against the oracle in a container without a GPU.
+// Nothing in the product loads this library; it is built and used by tests/test_rules_host.py alone.
+#include "../../alphazero_quoridor_b200/csrc/qz_rules.cuh"
+
+extern "C" {
+
+void qh_initial(uint64_t *s3) { QzState s = qz_initial_state(); s3[0] = s.H; s3[1] = s.V; s3[2] = s.meta; }
+
+uint64_t qh_pack_meta(int p1, int p2, int w1, int w2, int cur, unsigned flags, unsigned ply) {
+    return qz_pack_meta(p1, p2, w1, w2, cur, flags, ply);
+}
+
+void qh_apply(uint64_t *s3, int action) {
+    QzState s{s3[0], s3[1], s3[2]};
+    s = qz_apply(s, action);
+    s3[0] = s.H; s3[1] = s.V; s3[2] = s.meta;
+}
+
+void qh_legal_mask(const uint64_t *s3, uint64_t *mask3) {
+    QzState s{s3[0], s3[1], s3[2]};
+    qz_legal_mask_seq(s, mask3);
+}
+
+unsigned qh_pawn_moves(uint64_t H, uint64_t V, int L, int O, int player) { return qz_pawn_moves(H, V, L, O, player); }
+
+// plain-move bits (N,S,E,W) of every tile from the direction masks, opponent ignored
+void qh_dirs(uint64_t H, uint64_t V, unsigned char *out81) {
+    QzDirs d = qz_dirs(H, V);
+    for (int t = 0; t < 81; t++)
+        out81[t] = (unsigned char)((bb_test(d.n, t) ? 1 : 0) | (bb_test(d.s, t) ? 2 : 0) | (bb_test(d.e, t) ? 4 : 0) |
+                                   (bb_test(d.w, t) ? 8 : 0));
+}
+
+// same, but built incrementally: masks of (H0,V0) then one wall placed through qz_dirs_place_*
+void qh_dirs_incremental(uint64_t H0, uint64_t V0, int ix, int vertical, unsigned char *out81) {
+    QzDirs d = qz_dirs(H0, V0);
+    if (vertical) qz_dirs_place_v(d, ix); else qz_dirs_place_h(d, ix);
+    for (int t = 0; t < 81; t++)
+        out81[t] = (unsigned char)((bb_test(d.n, t) ? 1 : 0) | (bb_test(d.s, t) ? 2 : 0) | (bb_test(d.e, t) ? 4 : 0) |
+                                   (bb_test(d.w, t) ? 8 : 0));
+}
+
+void qh_spread8(uint64_t x, uint32_t *w3) { BB b = bb_spread8(x); w3[0] = b.w0; w3[1] = b.w1; w3[2] = b.w2; }
+
+void qh_encode(const uint64_t *s3, float *out) {
+    QzState s{s3[0], s3[1], s3[2]};
+    for (int p = 0; p < 26; p++)
+        for (int r = 0; r < 9; r++)
+            for (int c = 0; c < 9; c++) out[p * 81 + r * 9 + c] = (float)qz_plane_value(s, p, r, c);
+}
+
+int qh_action_rank(const uint64_t *mask3, int a) {
+    uint32_t pawn; uint64_t hl, vl;
+    qz_unpack_mask(mask3, pawn, hl, vl);
+    return qz_action_rank(pawn, hl, vl, a);
+}
+
+int qh_nth_bit64(uint64_t m, int k) { return qz_nth_bit64(m, k); }
+int qh_delta(int a) { return qz_delta(a); }
+}
