@@ -23,8 +23,10 @@
 
 #if defined(__CUDACC__)
 #define QZ_HD __host__ __device__ __forceinline__
+#define QZ_HD_NOINLINE static __host__ __device__ __noinline__
 #else
 #define QZ_HD static inline
+#define QZ_HD_NOINLINE static
 #endif
 
 struct QzState {
@@ -316,7 +318,7 @@ QZ_HD int qz_delta(int a) {
 // u32: byte i = actions 4..11 available from source tile O + QZ_SRC[i]  (i: 0 = O-9, 1 = O+9, 2 = O-1, 3 = O+1).
 QZ_HD int qz_jump_src(int O, int i) { return O + (i == 0 ? -9 : (i == 1 ? 9 : (i == 2 ? -1 : 1))); }
 
-QZ_HD uint32_t qz_jump_set(uint64_t H, uint64_t V, int O, int player) {
+QZ_HD_NOINLINE uint32_t qz_jump_set(uint64_t H, uint64_t V, int O, int player) {
     uint32_t js = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {

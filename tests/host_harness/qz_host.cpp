@@ -59,3 +59,22 @@ int qh_action_rank(const uint64_t *mask3, int a) {
 int qh_nth_bit64(uint64_t m, int k) { return qz_nth_bit64(m, k); }
 int qh_delta(int a) { return qz_delta(a); }
 }
+
+#include "../../alphazero_quoridor_b200/csrc/qz_sample.cuh"
+extern "C" {
+void qh_philox(uint64_t seed, uint64_t rid, uint32_t c2, uint32_t c3, uint32_t *out4) {
+    QzPhilox4 b = qz_philox(seed, rid, c2, c3);
+    out4[0] = b.x; out4[1] = b.y; out4[2] = b.z; out4[3] = b.w;
+}
+int qh_sample_action(const uint64_t *s3, uint64_t seed, uint64_t rid, uint32_t ply) {
+    QzState s{s3[0], s3[1], s3[2]};
+    QzRng rng = qz_rng_init(seed, rid);
+    return qz_sample_action(s, rng, ply);
+}
+int qh_rollout(uint64_t *s3, uint64_t seed, uint64_t rid, int limit, int *plies) {
+    QzState s{s3[0], s3[1], s3[2]};
+    int v = qz_rollout(s, seed, rid, limit, *plies);
+    s3[0] = s.H; s3[1] = s.V; s3[2] = s.meta;
+    return v;
+}
+}

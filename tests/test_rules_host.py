@@ -252,3 +252,50 @@ def test_random_games_vs_oracle(qh):
             if done:
                 assert ((m["flags"] >> 1) & 3) == g.has_a_winner()[1]
                 break
+
+
+def test_philox_and_rollouts_match_oracle(qh):
+    """The sampled-legality rollout (qz_sample.cuh) == oracle rollout built on the literal rules."""
+    qh.qh_philox.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint32)]
+    qh.qh_sample_action.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_uint32]
+    qh.qh_rollout.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_int)]
+    rng = random.Random(8)
+    for _ in range(200):
+        seed, rid, c2, c3 = rng.getrandbits(64), rng.getrandbits(64), rng.getrandbits(32), rng.getrandbits(32)
+        out = (C.c_uint32 * 4)()
+        qh.qh_philox(seed, rid, c2, c3, out)
+        assert list(out) == O.philox(seed, rid, c2, c3)
+    # Philox4x32-10 known-answer vectors (Random123 kat_vectors): zero and all-ones inputs
+    out = (C.c_uint32 * 4)()
+    qh.qh_philox(0, 0, 0, 0, out)
+    assert [hex(x) for x in out] == ['0x6627e8d5', '0xe169c58d', '0xbc57ac4c', '0x9b00dbd8']
+    qh.qh_philox(M64, M64, 0xFFFFFFFF, 0xFFFFFFFF, out)
+    assert [hex(x) for x in out] == ['0x408f276d', '0x41c83b0e', '0xa20bc7c6', '0x6d5451fd']
+    # single draws on walled positions
+    for it in range(600):
+        H, V, p1, p2, w1, w2, cur = _random_position(rng)
+        s = mk_state(qh, H, V, p1, p2, w1, w2, cur)
+        g = O.OracleGame().set_position(H, V, p1, p2, w1, w2, cur)
+        seed, rid, ply = rng.getrandbits(64), rng.getrandbits(40), rng.randrange(0, 900)
+        assert qh.qh_sample_action(s, seed, rid, ply) == g.sample_action(seed, rid, ply)
+    # whole rollouts from the start and from midgames
+    for it in range(150):
+        if it < 60:
+            s = (C.c_uint64 * 3)()
+            qh.qh_initial(s)
+            g = O.OracleGame()
+        else:
+            H, V, p1, p2, w1, w2, cur = _random_position(rng)
+            s = mk_state(qh, H, V, p1, p2, w1, w2, cur)
+            g = O.OracleGame().set_position(H, V, p1, p2, w1, w2, cur)
+        seed, rid = rng.getrandbits(64), it
+        plies = C.c_int()
+        v = qh.qh_rollout(s, seed, rid, 1000, C.byref(plies))
+        want_v, want_plies = g.rollout(seed, rid, 1000)
+        assert (v, plies.value) == (want_v, want_plies)
+        pos = g.position()
+        m = unpack_meta(s[2])
+        assert (s[0], s[1], m["p1"], m["p2"]) == (pos["H"], pos["V"], pos["p1"], pos["p2"])
+
+
+M64 = (1 << 64) - 1
