@@ -35,6 +35,13 @@ SIGNATURES = {
     "qz_env_legal_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
     "qz_env_encode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _i64, _vp]),
     "qz_rollout": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qz_mcts_init": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "qz_mcts_select": (C.c_int, [_vp, _f64, C.c_int, C.c_int, _vp]),
+    "qz_mcts_expand_backup": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "qz_mcts_root_stats": (C.c_int, [_vp, _f64, _vp, _vp, _vp, _vp, _vp]),
+    "qz_mcts_choose": (C.c_int, [_vp, C.c_int, _f64, _f64, _f64, _u64, _vp, _vp, _vp]),
+    "qz_mcts_reroot": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "qz_stub_eval": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _vp]),
 }
 
 

@@ -1,0 +1,189 @@
+"""Drop-in for the reference's mcts.py: `softmax`, `MCTS`, `MCTSPlayer` -- same constructors, methods, return
+types and defaults (mcts.py:6-199) -- running the tree on the GPU through `tree.BatchedMCTS` (batch of one).
+
+`policy_value_fn(game)` keeps the reference's contract (policy_value_net.py:145-164): it receives a
+`Quoridor`-like object positioned at the leaf and returns `(iterable[(action, prob)], value)`.
+Three kinds of callables are accepted:
+  * any Python callable  -> called once per leaf on a host `Quoridor` view of the leaf (API-compatible, slow);
+  * `DeviceStub(kind)`   -> the parity stubs S1/S2/S3 evaluated by a kernel (no host round trip per leaf);
+  * `PolicyValueNet.policy_value_fn` of this package -> the net's batched device path.
+For throughput use `tree.BatchedMCTS` / `selfplay.BatchedSelfPlay` with thousands of games instead.
+"""
+import numpy as np
+import torch
+
+from . import tree as _tree
+from .quoridor import Quoridor, mask_to_actions, unpack_meta
+
+M64 = (1 << 64) - 1
+
+
+def softmax(x):
+    """mcts.py:6-9"""
+    probs = np.exp(x - np.max(x))
+    probs /= np.sum(probs)
+    return probs
+
+
+class DeviceStub:
+    """A policy_value_fn that the engine evaluates on the device (tests/golden/stubs.py S1/S2/S3).
+    Calling it from Python raises: it only exists to select the kernel."""
+
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __call__(self, game):
+        raise RuntimeError("DeviceStub is evaluated by the qz_stub_eval kernel, not called from Python")
+
+
+def _game_from_state(row):
+    """Host `Quoridor` view of a qz_state row (for Python policy callbacks)."""
+    H, V, m = [int(x) & M64 for x in row]
+    d = unpack_meta(m)
+    g = Quoridor()
+    for ix in range(64):
+        g._intersections[ix] = 1 if (H >> ix) & 1 else (-1 if (V >> ix) & 1 else 0)
+    g._positions = {1: d["p1"], 2: d["p2"]}
+    g._player1_walls_remaining, g._player2_walls_remaining = d["w1"], d["w2"]
+    g.current_player = d["cur"]
+    g.last_player = 3 - d["cur"]
+    g._ply = d["ply"]
+    return g
+
+
+class _CallbackEvaluator:
+    """Evaluates leaves by calling the user's Python policy_value_fn (mcts.py:117)."""
+
+    def __init__(self, fn):
+        self.fn = fn
+
+    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
+        m = leaf_states.shape[0]
+        rows = leaf_states.cpu().numpy()
+        flags = mcts.leaf_flags.cpu().numpy()
+        priors = np.zeros((m, 140), dtype=np.float32)
+        values = np.zeros((m,), dtype=np.float64)
+        for i in range(m):
+            if flags[i] & (_tree.LEAF_INACTIVE | _tree.LEAF_TERMINAL):
+                continue        # reference calls the policy on terminal leaves too but discards the result
+            act_probs, v = self.fn(_game_from_state(rows[i]))
+            for a, p in act_probs:
+                priors[i, int(a)] = np.float32(p)
+            values[i] = float(v)
+        dev = leaf_states.device
+        return dict(priors=torch.from_numpy(priors).to(dev), value_f64=torch.from_numpy(values).to(dev))
+
+
+def _make_evaluator(policy_value_fn):
+    if isinstance(policy_value_fn, DeviceStub):
+        return _tree.StubEvaluator(policy_value_fn.kind)
+    owner = getattr(policy_value_fn, "__self__", None)
+    if owner is not None and hasattr(owner, "evaluate_states") and getattr(policy_value_fn, "__name__", "") == "policy_value_fn":
+        return _tree.NetEvaluator(owner)
+    return _CallbackEvaluator(policy_value_fn)
+
+
+class MCTS(object):
+    """mcts.py:83-154"""
+
+    def __init__(self, policy_value_fn, c_puct=5, n_playout=1800, leaves_per_game=1, fix_terminal_sign=False,
+                 device=None):
+        self._policy = policy_value_fn
+        self._c_puct = c_puct
+        self._n_playout = n_playout
+        self._engine = _tree.BatchedMCTS(1, _make_evaluator(policy_value_fn), c_puct=c_puct, n_playout=n_playout,
+                                         leaves_per_game=leaves_per_game, fix_terminal_sign=fix_terminal_sign,
+                                         reuse_tree=True, device=device)
+        self._fresh = True
+        self._engine.reset(torch.tensor([Quoridor().packed()], dtype=torch.int64))
+
+    def _set_root_state(self, game):
+        row = torch.tensor([game.packed()], dtype=torch.int64, device=self._engine.device)
+        self._engine.root_state.copy_(row)
+
+    def get_move_probs(self, game, temp=1e-3):
+        """mcts.py:129-144: n_playout playouts from `game`, then (acts, probs) over the root's children in
+        insertion (= actions()) order."""
+        self._set_root_state(game)
+        self._engine.search(self._n_playout)
+        visits140, _, _ = self._engine.root_stats(temp=max(float(temp), 1e-12))
+        acts, visits = self._root_children(visits140)
+        act_probs = softmax(1.0 / temp * np.log(np.array(visits) + 1e-10))
+        return tuple(acts), act_probs
+
+    def _root_children(self, visits140=None):
+        """(acts in child order, visits) of the root."""
+        eng = self._engine
+        a = eng.arena
+        root = int(a.root[0].item())
+        base = int(a.child_base[root].item())
+        if base < 0:
+            return [], []
+        nc = (int(a.node_meta[root].item()) >> 8) & 0xFF
+        meta = a.node_meta[base:base + nc].cpu().numpy()
+        acts = [int(x) & 0xFF for x in meta]
+        visits = [int(x) for x in a.visits[base:base + nc].cpu().numpy()]
+        return acts, visits
+
+    def root_children_stats(self):
+        """(acts, visits, Q) of the root's children plus (root visits, root Q) -- for tests / inspection."""
+        eng = self._engine
+        a = eng.arena
+        root = int(a.root[0].item())
+        base = int(a.child_base[root].item())
+        rn, rq = int(a.visits[root].item()), float(a.q[root].item())
+        if base < 0:
+            return [], [], [], rn, rq
+        nc = (int(a.node_meta[root].item()) >> 8) & 0xFF
+        acts = [int(x) & 0xFF for x in a.node_meta[base:base + nc].cpu().numpy()]
+        visits = [int(x) for x in a.visits[base:base + nc].cpu().numpy()]
+        qs = [float(x) for x in a.q[base:base + nc].cpu().numpy()]
+        return acts, visits, qs, rn, rq
+
+    def update_with_move(self, last_move):
+        """mcts.py:146-151"""
+        mv = torch.tensor([int(last_move)], dtype=torch.int32)
+        # the root state is re-read from the caller's game at the next get_move_probs, as in the reference
+        self._engine.advance(mv, keep_subtree=True)
+
+    def __str__(self):
+        return "MCTS"
+
+
+class MCTSPlayer(object):
+    """mcts.py:157-199"""
+
+    def __init__(self, policy_value_function, c_puct=5, n_playout=2000, is_selfplay=0, **engine_kwargs):
+        self.mcts = MCTS(policy_value_function, c_puct, n_playout, **engine_kwargs)
+        self._is_selfplay = is_selfplay
+
+    def set_player_ind(self, p):
+        self.player = p
+
+    def reset_player(self):
+        self.mcts.update_with_move(-1)
+
+    def choose_action(self, game, temp=1e-3, return_prob=0):
+        sensible_moves = game.actions()
+        move_probs = np.zeros(140)
+        if len(sensible_moves) > 0:
+            acts, probs = self.mcts.get_move_probs(game, temp)
+            move_probs[list(acts)] = probs
+            if self._is_selfplay:
+                # mcts.py:181: Dirichlet noise on the MOVE distribution (not on the root priors)
+                move = np.random.choice(acts, p=0.75 * probs + 0.25 * np.random.dirichlet(0.3 * np.ones(len(probs))))
+                self.mcts.update_with_move(move)
+            else:
+                move = np.random.choice(acts, p=probs)
+                self.mcts.update_with_move(-1)
+            if return_prob:
+                return move, move_probs
+            return move
+        # mcts.py:195-196: the reference prints a warning and returns None
+        return None
+
+    # BASELINE.json's north_star calls this `get_action`; the reference method is choose_action (mcts.py:172)
+    get_action = choose_action
+
+    def __str__(self):
+        return "MCTS {}".format(self.player)

@@ -1,0 +1,260 @@
+"""Batched PUCT MCTS on the GPU: the engine behind `mcts.MCTS` / `pure_mcts.MCTS` (mcts.py, pure_mcts.py).
+
+`BatchedMCTS` owns the flat tree arrays (torch CUDA tensors) of n concurrent games and drives the
+select -> legal-mask -> evaluate -> expand+backup kernels of libqzb200.so.  Evaluators:
+
+* `StubEvaluator(kind)`     deterministic parity stubs S1/S2/S3 (tests/golden/stubs.py), on the device
+* `RolloutEvaluator(seed)`  pure MCTS: uniform priors + random rollout (pure_mcts.py:13-16,86-108)
+* `NetEvaluator(net)`       the 5-block ResNet in PyTorch bf16 (policy_value_net.py), leaves encoded straight
+                            into its input tensor by the encode kernel
+
+With `leaves_per_game=1` the search is the reference's sequential algorithm, one playout per game per wave,
+and visit counts match the reference exactly under a deterministic evaluator; `leaves_per_game=K>1` collects K
+leaves per game per wave with virtual loss (a documented deviation that trades exactness for batch size).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .rollout import rollout as _rollout
+
+LEAF_TERMINAL, LEAF_DEPTH_OVERFLOW, LEAF_ARENA_OVERFLOW, LEAF_DUPLICATE, LEAF_INACTIVE = 1, 2, 4, 8, 16
+MAX_CHILDREN = 140
+
+
+class QzTree(C.Structure):
+    """struct qz_tree of include/qzb200.h."""
+    _fields_ = [("n_games", C.c_int64), ("node_cap", C.c_int32), ("max_depth", C.c_int32),
+                ("leaves_per_game", C.c_int32), ("reserved", C.c_int32),
+                ("prior", C.c_void_p), ("visits", C.c_void_p), ("q", C.c_void_p), ("child_base", C.c_void_p),
+                ("node_meta", C.c_void_p), ("root", C.c_void_p), ("n_nodes", C.c_void_p),
+                ("root_state", C.c_void_p), ("leaf_node", C.c_void_p), ("leaf_state", C.c_void_p),
+                ("path", C.c_void_p), ("path_len", C.c_void_p), ("leaf_flags", C.c_void_p)]
+
+
+class _Arena:
+    """One set of node arrays for n games (a second one is the re-root compaction target)."""
+
+    def __init__(self, n, cap, dev):
+        tot = n * cap
+        self.prior = torch.empty(tot, dtype=torch.float32, device=dev)
+        self.visits = torch.empty(tot, dtype=torch.int32, device=dev)
+        self.q = torch.empty(tot, dtype=torch.float64, device=dev)
+        self.child_base = torch.empty(tot, dtype=torch.int32, device=dev)
+        self.node_meta = torch.empty(tot, dtype=torch.int32, device=dev)
+        self.root = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.n_nodes = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.root_state = torch.zeros((n, 3), dtype=torch.int64, device=dev)
+
+    def nbytes(self):
+        return sum(t.numel() * t.element_size() for t in vars(self).values() if torch.is_tensor(t))
+
+
+# ------------------------------------------------------------------------------------------------ evaluators
+class StubEvaluator:
+    """Parity stubs evaluated by the qz_stub_eval kernel.  kind: 1 = S1 uniform, 2 = S2 hash, 3 = S3 hash/8."""
+
+    def __init__(self, kind):
+        self.kind = {"S1": 1, "S2": 2, "S3": 3}.get(kind, kind)
+        self._buf = None
+
+    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
+        m = leaf_states.shape[0]
+        if self._buf is None or self._buf[0].shape[0] != m:
+            self._buf = (torch.empty((m, 140), dtype=torch.float32, device=leaf_states.device),
+                         torch.empty((m,), dtype=torch.float64, device=leaf_states.device))
+        priors, values = self._buf
+        _lib.check(mcts.lib.qz_stub_eval(_lib.ptr(leaf_states), _lib.ptr(masks), self.kind, _lib.ptr(priors),
+                                         _lib.ptr(values), m, mcts._stream()), "qz_stub_eval")
+        return dict(priors=priors, value_f64=values)
+
+
+class RolloutEvaluator:
+    """pure_mcts.policy_value_fn + _evaluate_rollout: uniform priors, value = random playout (<= limit-1 plies)."""
+
+    uniform_prior = True
+
+    def __init__(self, seed=0, limit=1000):
+        self.seed, self.limit = seed, limit
+        self.env_steps = 0
+        self.count_steps = False
+        self._ws = None
+
+    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
+        if self._ws is None:
+            self._ws = torch.empty((2,), dtype=torch.int64, device=leaf_states.device)
+        res, plies, _ = _rollout(leaf_states, seed=self.seed, rids=leaf_rids,
+                                 state_index=mcts._leaf_iota, limit=self.limit,
+                                 return_plies=self.count_steps, workspace=self._ws)
+        if self.count_steps:
+            self.env_steps = self.env_steps + plies.sum(dtype=torch.int64)
+        return dict(priors=None, value_i8=res)
+
+
+class NetEvaluator:
+    """Leaf evaluation by the policy-value net (policy_value_net.py:145-164 contract, batched).
+    `net` is an alphazero_quoridor_b200.policy_value_net.PolicyValueNet."""
+
+    def __init__(self, net):
+        self.net = net
+
+    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
+        probs, value = self.net.evaluate_states(leaf_states)
+        return dict(priors=probs, value_f32=value)
+
+
+# ------------------------------------------------------------------------------------------------ the search
+class BatchedMCTS:
+    def __init__(self, n_games, evaluator, c_puct=5, n_playout=100, leaves_per_game=1, node_cap=None,
+                 max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.n = int(n_games)
+        self.K = int(leaves_per_game)
+        self.c_puct = float(c_puct)
+        self.n_playout = int(n_playout)
+        self.evaluator = evaluator
+        self.uniform_prior = bool(getattr(evaluator, "uniform_prior", False))
+        self.fix_terminal_sign = bool(fix_terminal_sign)
+        self.max_depth = int(max_depth)
+        if node_cap is None:
+            node_cap = 1 + (self.n_playout * (2 if reuse_tree else 1) + self.K) * 132
+        self.node_cap = int(node_cap)
+        dev = self.device
+        self.arenas = [_Arena(self.n, self.node_cap, dev)]
+        if reuse_tree:
+            self.arenas.append(_Arena(self.n, self.node_cap, dev))
+        self.cur = 0
+        m = self.n * self.K
+        self.leaf_node = torch.empty(m, dtype=torch.int32, device=dev)
+        self.leaf_state = torch.zeros((m, 3), dtype=torch.int64, device=dev)
+        self.path = torch.empty(m * self.max_depth, dtype=torch.int32, device=dev)
+        self.path_len = torch.empty(m, dtype=torch.int32, device=dev)
+        self.leaf_flags = torch.zeros(m, dtype=torch.uint8, device=dev)
+        self.leaf_mask = torch.zeros((m, 3), dtype=torch.int64, device=dev)
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._leaf_iota = torch.arange(m, dtype=torch.int32, device=dev)
+        self._k_of_leaf = (torch.arange(m, dtype=torch.int64, device=dev) % self.K)
+        # RNG stream id of game g (rollouts, move sampling); callers set it to a GLOBAL game index so that
+        # results do not depend on how games are sharded over GPUs
+        self.game_id = torch.arange(self.n, dtype=torch.int64, device=dev)
+        self.playouts_done = 0       # playouts since the last reset/advance (per game)
+        self.total_playouts = 0
+        self._structs = [self._make_struct(a) for a in self.arenas]
+
+    # ---- plumbing ----
+    def _stream(self):
+        return _lib.stream_ptr(self.device)
+
+    def _make_struct(self, a):
+        t = QzTree()
+        t.n_games, t.node_cap, t.max_depth, t.leaves_per_game, t.reserved = self.n, self.node_cap, self.max_depth, self.K, 0
+        for name in ("prior", "visits", "q", "child_base", "node_meta", "root", "n_nodes", "root_state"):
+            setattr(t, name, getattr(a, name).data_ptr())
+        for name in ("leaf_node", "leaf_state", "path", "path_len", "leaf_flags"):
+            setattr(t, name, getattr(self, name).data_ptr())
+        return t
+
+    @property
+    def tree(self):
+        return self._structs[self.cur]
+
+    @property
+    def arena(self):
+        return self.arenas[self.cur]
+
+    @property
+    def root_state(self):
+        return self.arena.root_state
+
+    def nbytes(self):
+        return sum(a.nbytes() for a in self.arenas)
+
+    # ---- reference operations ----
+    def reset(self, root_states, select=None):
+        """Fresh trees (mcts.py:97 / update_with_move(-1)) rooted at `root_states` (int64 [n,3])."""
+        root_states = root_states.to(self.device).contiguous()
+        assert root_states.shape == (self.n, 3)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qz_mcts_init(C.byref(self.tree), _lib.ptr(root_states), _lib.ptr(select),
+                                             self._stream()), "qz_mcts_init")
+        self.playouts_done = 0
+
+    def playout_wave(self, k_leaves=None):
+        """One wave: k_leaves playouts per game (mcts.py:103-127)."""
+        k = self.K if k_leaves is None else int(k_leaves)
+        with torch.cuda.device(self.device):
+            st = self._stream()
+            _lib.check(self.lib.qz_mcts_select(C.byref(self.tree), self.c_puct, int(self.uniform_prior), k, st),
+                       "qz_mcts_select")
+            m = self.n * self.K
+            _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(self.leaf_state), _lib.ptr(self.leaf_mask), m, st),
+                       "qz_env_legal_mask")
+            # rollout / RNG stream of leaf (g,k): unique per (game, playout)
+            rids = None
+            if getattr(self.evaluator, "uniform_prior", False):
+                rids = (self.game_id.repeat_interleave(self.K) + (self.total_playouts + self._k_of_leaf))
+            ev = self.evaluator.evaluate(self, self.leaf_state, self.leaf_mask, rids)
+            _lib.check(self.lib.qz_mcts_expand_backup(
+                C.byref(self.tree), _lib.ptr(self.leaf_mask), _lib.ptr(ev.get("priors")),
+                _lib.ptr(ev.get("value_f32")), _lib.ptr(ev.get("value_f64")), _lib.ptr(ev.get("value_i8")),
+                int(self.fix_terminal_sign), _lib.ptr(self.overflow), st), "qz_mcts_expand_backup")
+        self.playouts_done += k
+        self.total_playouts += k
+
+    def search(self, n_playout=None):
+        """get_move_probs' loop (mcts.py:135-139): n_playout playouts for every game."""
+        total = self.n_playout if n_playout is None else int(n_playout)
+        done = 0
+        while done < total:
+            k = min(self.K, total - done)
+            self.playout_wave(k)
+            done += k
+
+    def root_stats(self, temp=1e-3, want_q=False):
+        """(visits int32 [n,140], probs float64 [n,140], root_visits int32 [n][, q float64 [n,140]])
+        -- mcts.py:141-144 scattered by action id."""
+        dev = self.device
+        visits = torch.empty((self.n, 140), dtype=torch.int32, device=dev)
+        probs = torch.empty((self.n, 140), dtype=torch.float64, device=dev)
+        rootn = torch.empty((self.n,), dtype=torch.int32, device=dev)
+        q = torch.empty((self.n, 140), dtype=torch.float64, device=dev) if want_q else None
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.qz_mcts_root_stats(C.byref(self.tree), float(temp), _lib.ptr(visits), _lib.ptr(q),
+                                                   _lib.ptr(probs), _lib.ptr(rootn), self._stream()),
+                       "qz_mcts_root_stats")
+        return (visits, probs, rootn, q) if want_q else (visits, probs, rootn)
+
+    def choose(self, mode=0, temp=1e-3, seed=0, noise_eps=0.25, dir_alpha=0.3):
+        """Moves int32 [n] (mcts.py:177-187 / pure_mcts.py:115).  mode 0 first-max visits, 1 sample from probs,
+        2 sample from (1-eps)*probs + eps*Dirichlet(alpha)."""
+        moves = torch.empty((self.n,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qz_mcts_choose(C.byref(self.tree), int(mode), float(temp), float(noise_eps),
+                                               float(dir_alpha), int(seed) & ((1 << 64) - 1), _lib.ptr(self.game_id),
+                                               _lib.ptr(moves), self._stream()), "qz_mcts_choose")
+        return moves
+
+    def advance(self, moves, keep_subtree=True):
+        """update_with_move (mcts.py:146-151) for every game and step the root states by `moves`.
+        keep_subtree=False (or a negative move) discards the tree (pure_mcts.py:142)."""
+        moves = moves.to(device=self.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(self.device):
+            if keep_subtree and len(self.arenas) == 2:
+                src, dst = self._structs[self.cur], self._structs[1 - self.cur]
+                _lib.check(self.lib.qz_mcts_reroot(C.byref(src), C.byref(dst), _lib.ptr(moves), 1, self._stream()),
+                           "qz_mcts_reroot")
+                self.cur = 1 - self.cur
+            else:
+                st = self._stream()
+                _lib.check(self.lib.qz_env_step(_lib.ptr(self.arena.root_state), _lib.ptr(moves), None, None, self.n, st),
+                           "qz_env_step")
+                _lib.check(self.lib.qz_mcts_init(C.byref(self.tree), None, None, st), "qz_mcts_init")
+        self.playouts_done = 0
+
+    def overflow_count(self):
+        return int(self.overflow.item())

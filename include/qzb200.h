@@ -125,6 +125,87 @@ int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_in
                int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
                int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, void *stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched PUCT MCTS (mcts.py, pure_mcts.py).  n_games trees live in flat, caller-owned device arrays.
+ *
+ * qz_tree is a HOST struct of device pointers and sizes, passed by pointer and copied by the call.
+ * Game g owns node slots [g*node_cap, (g+1)*node_cap); a node's children are contiguous and stored in
+ * the reference's actions() order (so mcts.py:42's first-max tie-break is "lowest child index").
+ *   per node : prior f32 (TreeNode._P), visits i32 (_n_visits), q f64 (_Q), child_base i32 (-1 = is_leaf()),
+ *              node_meta u32 = action | n_children << 8 | in-flight (virtual loss) count << 16
+ *   per game : root (node index, always 0 after init/reroot), n_nodes (bump allocator), root_state
+ *   per leaf : (n_games * leaves_per_game entries, refilled by every select) leaf_node, leaf_state,
+ *              path[max_depth] + path_len (root..leaf node indices), leaf_flags (QZ_LEAF_*)
+ */
+typedef struct qz_tree {
+    int64_t n_games;
+    int32_t node_cap;
+    int32_t max_depth;
+    int32_t leaves_per_game;
+    int32_t reserved;
+    float *prior;
+    int32_t *visits;
+    double *q;
+    int32_t *child_base;
+    uint32_t *node_meta;
+    int32_t *root;
+    int32_t *n_nodes;
+    qz_state *root_state;
+    int32_t *leaf_node;
+    qz_state *leaf_state;
+    int32_t *path;
+    int32_t *path_len;
+    uint8_t *leaf_flags;
+} qz_tree;
+
+#define QZ_LEAF_TERMINAL 0x01       /* the game is over at the leaf (never sent to the evaluator's result) */
+#define QZ_LEAF_DEPTH_OVERFLOW 0x02 /* descent stopped at max_depth */
+#define QZ_LEAF_ARENA_OVERFLOW 0x04 /* children did not fit node_cap; leaf left unexpanded */
+#define QZ_LEAF_DUPLICATE 0x08      /* another leaf of the same wave expanded this node first */
+#define QZ_LEAF_INACTIVE 0x10       /* slot k >= k_leaves of this wave */
+
+/* MCTS.__init__ (mcts.py:89-100) / update_with_move(-1) (:150-151): fresh root (prior 1.0) for every game
+ * (or only those with select[g] != 0); root_states (nullable) are copied into tree->root_state. */
+int qz_mcts_init(const qz_tree *tree, const qz_state *root_states, const uint8_t *select, void *stream);
+
+/* The descent of MCTS._playout (mcts.py:107-113; pure_mcts.py:68-73): for each game, k_leaves (<=
+ * leaves_per_game) descents from the root by first-max of Q + c_puct*P*sqrt(N_parent)/(1+n) (TreeNode.select /
+ * get_value, mcts.py:37-42,64-70), replaying Quoridor.step from root_state.  Fills the per-leaf arrays.
+ * uniform_prior != 0: priors are 1/len(children) in float64 (pure_mcts.py:13-16) instead of the stored f32.
+ * With k_leaves > 1 later descents see a virtual loss on earlier paths (deviation; k_leaves = 1 is exact). */
+int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, void *stream);
+
+/* The rest of MCTS._playout (mcts.py:117-127): for every leaf of the last select, unless terminal, expand
+ * with (action, prior) over the legal actions in actions() order (TreeNode.expand, mcts.py:27-35; priors
+ * [n*K,140] are read at the legal actions only and NOT renormalised, policy_value_net.py:162; NULL = uniform)
+ * and back up -leaf_value along the path with a sign flip per level (update_recursive, mcts.py:44-62).
+ * Exactly one of value_f32 / value_f64 / value_i8 is the evaluator's value for the side to move.  Terminal
+ * leaves use +1 (the reference's inverted sign, mcts.py:125) or -1 when fix_terminal_sign != 0. */
+int qz_mcts_expand_backup(const qz_tree *tree, const uint64_t *mask3, const float *priors, const float *value_f32,
+                          const double *value_f64, const int8_t *value_i8, int fix_terminal_sign,
+                          int32_t *overflow_count, void *stream);
+
+/* get_move_probs (mcts.py:141-144): per game, root-child visit counts / Q scattered by action id into
+ * [n,140] arrays (nullable each), softmax(1/temp*log(visits+1e-10)) in float64, and the root's own visits. */
+int qz_mcts_root_stats(const qz_tree *tree, double temp, int32_t *visits_out, double *q_out, double *probs_out,
+                       int32_t *root_n_out, void *stream);
+
+/* MCTSPlayer.choose_action (mcts.py:172-196) / pure_mcts get_move (:115).  mode 0: first max of visits;
+ * mode 1: sample from probs (:185); mode 2: sample from (1-noise_eps)*probs + noise_eps*Dirichlet(dir_alpha)
+ * (:181 uses 0.75/0.25 and 0.3).  Philox streams keyed by (seed, game_id[g] or g, ply).  -1 = no children. */
+int qz_mcts_choose(const qz_tree *tree, int mode, double temp, double noise_eps, double dir_alpha, uint64_t seed,
+                   const int64_t *game_id, int32_t *moves_out, void *stream);
+
+/* MCTS.update_with_move (mcts.py:146-151): dst := the subtree of src under moves[g] (statistics kept,
+ * compacted breadth-first) or a fresh root if the move is unknown / negative.  apply_move != 0 also advances
+ * root_state by the move (Quoridor.step).  src and dst must be distinct arenas of equal shape. */
+int qz_mcts_reroot(const qz_tree *src, const qz_tree *dst, const int32_t *moves, int apply_move, void *stream);
+
+/* Deterministic policy-value stubs for parity testing (tests/golden/stubs.py: kind 1 = S1 uniform, 2 = S2 hash,
+ * 3 = S3 hash/8) evaluated on the device: priors f32 [n,140] (0 at illegal actions), values f64 [n]. */
+int qz_stub_eval(const qz_state *states, const uint64_t *mask3, int kind, float *priors, double *values, int64_t n,
+                 void *stream);
+
 #ifdef __cplusplus
 }
 #endif

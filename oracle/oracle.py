@@ -54,6 +54,7 @@ def lib():
         L.oq_mcts_free.argtypes = [vp]
         L.oq_mcts_set_fix_terminal_sign.argtypes = [vp, C.c_int]
         L.oq_mcts_set_seed.argtypes = [vp, C.c_uint64]
+        L.oq_mcts_set_rollout_counter.argtypes = [vp, C.c_uint64]
         L.oq_mcts_env_steps.argtypes = [vp]
         L.oq_mcts_env_steps.restype = C.c_longlong
         L.oq_mcts_run.argtypes = [vp, vp, i32p, i32p, f64p]
@@ -167,11 +168,12 @@ def valid_pawn_actions(H, V, loc, opp, player):
 class OracleMCTS:
     """mcts.MCTS / pure_mcts.MCTS (stub_kind: 1 = S1, 2 = S2, 0 = pure MCTS with rollouts)."""
 
-    def __init__(self, stub_kind, c_puct=5, n_playout=100, fix_terminal_sign=False, seed=0):
+    def __init__(self, stub_kind, c_puct=5, n_playout=100, fix_terminal_sign=False, seed=0, rollout_counter=0):
         self._L = lib()
         self._t = C.c_void_p(self._L.oq_mcts_new(stub_kind, float(c_puct), n_playout))
         self._L.oq_mcts_set_fix_terminal_sign(self._t, int(fix_terminal_sign))
         self._L.oq_mcts_set_seed(self._t, seed)
+        self._L.oq_mcts_set_rollout_counter(self._t, rollout_counter)
 
     def __del__(self):
         try:

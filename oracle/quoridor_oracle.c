@@ -466,6 +466,7 @@ oq_mcts *oq_mcts_new(int stub_kind, double c_puct, int n_playout) {
 void oq_mcts_free(oq_mcts *t) { if (t) { node_free(t->root); free(t); } }
 void oq_mcts_set_fix_terminal_sign(oq_mcts *t, int f) { t->fix_terminal_sign = f; }
 void oq_mcts_set_seed(oq_mcts *t, uint64_t seed) { t->rng_seed = seed; t->rollout_counter = 0; }
+void oq_mcts_set_rollout_counter(oq_mcts *t, uint64_t c) { t->rollout_counter = c; }
 long long oq_mcts_env_steps(const oq_mcts *t) { return t->env_steps; }
 
 /* mcts.py:103-127 */

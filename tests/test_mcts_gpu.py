@@ -1,0 +1,246 @@
+"""GPU parity of the MCTS kernels (through the C ABI) against the golden fixtures (live reference) and the
+CPU oracle.  With one leaf per game per wave the search is the reference's sequential algorithm and root
+visit counts / Q must match EXACTLY under a deterministic evaluator (mcts.py:103-151).  With K > 1 leaves per
+wave (virtual loss) the stated tolerance is a total-variation bound on the root visit distribution."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+
+KIND = {"S1": 1, "S2": 2, "S3": 3}
+
+
+@pytest.fixture(scope="module")
+def qz():
+    import alphazero_quoridor_b200.mcts as m
+    import alphazero_quoridor_b200.pure_mcts as pm
+    import alphazero_quoridor_b200.quoridor as q
+    import alphazero_quoridor_b200.tree as t
+
+    class NS:
+        pass
+    ns = NS()
+    ns.mcts, ns.pure, ns.q, ns.tree = m, pm, q, t
+    return ns
+
+
+def _facade(qz, pos):
+    g = qz.q.Quoridor()
+    g._positions = {1: pos["p1"], 2: pos["p2"]}
+    for ix in range(64):
+        g._intersections[ix] = 1 if pos["H"] >> ix & 1 else (-1 if pos["V"] >> ix & 1 else 0)
+    g._player1_walls_remaining, g._player2_walls_remaining = pos["w1"], pos["w2"]
+    g.current_player = pos["cur"]
+    return g
+
+
+@pytest.mark.parametrize("idx", range(40))
+def test_mcts_golden_reference_api(qz, mcts_golden, idx):
+    """mcts.MCTS(policy, c_puct, n).get_move_probs / update_with_move vs the recorded reference runs."""
+    if idx >= len(mcts_golden):
+        pytest.skip("no such case")
+    case = mcts_golden[idx]
+    tree = qz.mcts.MCTS(qz.mcts.DeviceStub(case["stub"]), case["c_puct"], case["n_playout"])
+    g = _facade(qz, case["moves"][0]["pos"])
+    for i, mv in enumerate(case["moves"]):
+        acts, probs = tree.get_move_probs(g, case["temp"])
+        a2, visits, qs, rn, rq = tree.root_children_stats()
+        assert list(acts) == mv["acts"] == a2, case["name"]
+        assert visits == mv["visits"], case["name"]
+        assert qs == mv["q"], case["name"]                       # float64, bit-exact
+        assert (rn, rq) == (mv["root_visits"], mv["root_q"])
+        np.testing.assert_allclose(probs, np.array(mv["probs"]), rtol=1e-12, atol=1e-300)
+        if i + 1 < len(case["moves"]):
+            tree.update_with_move(mv["move"])
+            g.step(mv["move"])
+
+
+def _positions(n, seed, min_plies, max_plies):
+    from alphazero_quoridor_b200.synthetic import midgame_positions
+    return midgame_positions(n, seed=seed, min_plies=min_plies, max_plies=max_plies)
+
+
+def _host(qz, states):
+    hs = qz.q.BatchedQuoridor(states.shape[0], states=states).host_states()
+    H = np.array([d["H"] for d in hs], dtype=np.uint64)
+    V = np.array([d["V"] for d in hs], dtype=np.uint64)
+    meta5 = np.array([[d["p1"], d["p2"], d["w1"], d["w2"], d["cur"]] for d in hs], dtype=np.int32)
+    return hs, H, V, meta5
+
+
+@pytest.mark.parametrize("kind,n_playout,plies", [("S2", 48, (6, 18)), ("S3", 64, (14, 30)), ("S1", 40, (22, 60)),
+                                                   ("S3", 400, (40, 90))])
+def test_batched_stub_mcts_vs_oracle(qz, kind, n_playout, plies):
+    """Hundreds of independent trees searched side by side == the oracle's sequential search, exactly."""
+    n = 192
+    states = _positions(n, seed=21 + n_playout, min_plies=plies[0], max_plies=plies[1])
+    eng = qz.tree.BatchedMCTS(n, qz.tree.StubEvaluator(kind), c_puct=5, n_playout=n_playout, leaves_per_game=1,
+                              reuse_tree=False)
+    eng.reset(states)
+    eng.search()
+    visits, probs, rootn = eng.root_stats(temp=1.0)
+    _, H, V, meta5 = _host(qz, states)
+    _, want = O.stub_mcts_visits(H, V, meta5, n_playout, c_puct=5.0, stub_kind=KIND[kind])
+    assert np.array_equal(visits.cpu().numpy(), want)
+    assert (rootn.cpu().numpy() == n_playout).all()
+    assert eng.overflow_count() == 0
+    p = probs.cpu().numpy()
+    np.testing.assert_allclose(p.sum(1), 1.0, rtol=1e-12)
+
+
+def test_tree_reuse_and_moves_vs_oracle(qz):
+    """choose (first-max) + advance (re-root compaction) over several plies == oracle update_with_move."""
+    n, n_playout, n_moves = 96, 80, 6
+    states = _positions(n, seed=5, min_plies=24, max_plies=70)
+    eng = qz.tree.BatchedMCTS(n, qz.tree.StubEvaluator("S3"), c_puct=5, n_playout=n_playout, leaves_per_game=1,
+                              reuse_tree=True)
+    eng.reset(states)
+    hs, _, _, _ = _host(qz, states)
+    oracles = [O.OracleMCTS(3, 5, n_playout) for _ in range(n)]
+    games = [O.OracleGame().set_position(d["H"], d["V"], d["p1"], d["p2"], d["w1"], d["w2"], d["cur"]) for d in hs]
+    alive = [True] * n
+    for mv in range(n_moves):
+        eng.search()
+        visits, _, _ = eng.root_stats(temp=1.0)
+        visits = visits.cpu().numpy()
+        moves = eng.choose(mode=0).cpu().numpy()
+        for i in range(n):
+            if not alive[i]:
+                continue
+            acts, v, _ = oracles[i].run(games[i])
+            want = np.zeros(140, dtype=np.int32)
+            want[acts] = v
+            assert np.array_equal(visits[i], want), (mv, i)
+            best = acts[int(np.argmax(v))] if acts else -1
+            assert moves[i] == best
+            if best < 0:                       # stalemate: the reference would crash here
+                alive[i] = False
+                continue
+            oracles[i].update_with_move(best)
+            if games[i].step(best):
+                alive[i] = False
+        eng.advance(torch.from_numpy(moves))
+        # finished games keep being searched on the device (terminal root); only live ones are compared
+    assert sum(alive) > n // 2
+
+
+def test_fix_terminal_sign_switch(qz):
+    """fix_terminal_sign=True flips the reference's inverted terminal value; default keeps it."""
+    row = qz.q.pack_state(0, 0, 64, 40, 0, 0, 1)          # P1 one step from winning, no walls
+    st = torch.tensor([row], dtype=torch.int64)
+    res = {}
+    for fix in (False, True):
+        eng = qz.tree.BatchedMCTS(1, qz.tree.StubEvaluator("S1"), c_puct=5, n_playout=200, fix_terminal_sign=fix,
+                                  reuse_tree=False)
+        eng.reset(st)
+        eng.search()
+        v, _, _, q = eng.root_stats(temp=1.0, want_q=True)
+        res[fix] = (v[0, :4].cpu().tolist(), q[0, 0].item())
+        o = O.OracleMCTS(1, 5, 200, fix_terminal_sign=fix)
+        acts, ov, oq = o.run(O.OracleGame().set_position(0, 0, 64, 40, 0, 0, 1))
+        assert res[fix][0] == ov and res[fix][1] == oq[0]
+    assert res[False] == ([14, 86, 52, 47], -1.0)            # SURVEY.md 4 KAT "terminal sign"
+    assert res[True][1] == 1.0 and res[True][0][0] > 150     # the winning move dominates once the sign is fixed
+
+
+def test_virtual_loss_tolerance(qz):
+    """K = 8 leaves per wave vs the exact K = 1 search: mean total-variation distance of root visit
+    distributions <= 0.12 at 256 playouts (stated tolerance for the batched mode)."""
+    n, n_playout = 128, 256
+    states = _positions(n, seed=77, min_plies=10, max_plies=40)
+    out = {}
+    for K in (1, 8):
+        eng = qz.tree.BatchedMCTS(n, qz.tree.StubEvaluator("S3"), c_puct=5, n_playout=n_playout, leaves_per_game=K,
+                                  reuse_tree=False)
+        eng.reset(states)
+        eng.search()
+        v, _, rn = eng.root_stats(temp=1.0)
+        assert (rn.cpu().numpy() == n_playout).all()
+        out[K] = v.double().cpu().numpy()
+        assert (out[K].sum(1) == n_playout - 1).all()            # first playout only expands the root
+    tv = 0.5 * np.abs(out[1] / out[1].sum(1, keepdims=True) - out[8] / out[8].sum(1, keepdims=True)).sum(1)
+    print("virtual-loss TV: mean %.4f max %.4f" % (tv.mean(), tv.max()))
+    assert tv.mean() <= 0.12
+    same_best = (out[1].argmax(1) == out[8].argmax(1)).mean()
+    assert same_best >= 0.8
+
+
+def test_pure_mcts_vs_oracle(qz):
+    """Pure MCTS (uniform priors + rollouts, pure_mcts.py:66-115): same Philox rollout streams on both sides
+    => identical visit counts and chosen moves at K = 1."""
+    n, n_playout, seed = 48, 60, 99
+    states = _positions(n, seed=31, min_plies=8, max_plies=50)
+    ev = qz.tree.RolloutEvaluator(seed=seed)
+    eng = qz.tree.BatchedMCTS(n, ev, c_puct=5, n_playout=n_playout, leaves_per_game=1, reuse_tree=False)
+    eng.game_id.copy_(torch.arange(n, dtype=torch.int64) << 32)
+    eng.reset(states)
+    eng.search()
+    visits, _, _ = eng.root_stats(temp=1.0)
+    visits = visits.cpu().numpy()
+    moves = eng.choose(mode=0).cpu().numpy()
+    hs, _, _, _ = _host(qz, states)
+    for i, d in enumerate(hs):
+        g = O.OracleGame().set_position(d["H"], d["V"], d["p1"], d["p2"], d["w1"], d["w2"], d["cur"])
+        o = O.OracleMCTS(0, 5, n_playout, seed=seed, rollout_counter=i << 32)
+        acts, v, _ = o.run(g)
+        want = np.zeros(140, dtype=np.int32)
+        want[acts] = v
+        assert np.array_equal(visits[i], want), i
+        assert moves[i] == acts[int(np.argmax(v))]
+
+
+def test_python_callback_policy(qz, mcts_golden):
+    """An arbitrary Python policy_value_fn (the reference's contract) drives the same kernels."""
+    from stubs import make_stub
+    case = [c for c in mcts_golden if c["name"] == "terminal_sign"][0]
+    tree = qz.mcts.MCTS(make_stub("S1"), case["c_puct"], case["n_playout"])
+    g = _facade(qz, case["moves"][0]["pos"])
+    acts, probs = tree.get_move_probs(g, 1.0)
+    _, visits, qs, _, _ = tree.root_children_stats()
+    assert list(acts) == case["moves"][0]["acts"] and visits == case["moves"][0]["visits"]
+    assert qs == case["moves"][0]["q"]
+    case = [c for c in mcts_golden if c["name"] == "late_d_S2_cpuct1"][0]
+    tree = qz.mcts.MCTS(make_stub("S2"), case["c_puct"], 150)
+    dev = qz.mcts.MCTS(qz.mcts.DeviceStub("S2"), case["c_puct"], 150)
+    g = _facade(qz, case["moves"][0]["pos"])
+    tree.get_move_probs(g, 1.0)
+    dev.get_move_probs(g, 1.0)
+    assert tree.root_children_stats() == dev.root_children_stats()
+
+
+def test_players_and_self_play_loop(qz):
+    """MCTSPlayer.choose_action / get_action, pure MCTSPlayer, and Quoridor.start_self_play (quoridor.py:573-610)."""
+    np.random.seed(0)
+    g = qz.q.Quoridor()
+    player = qz.mcts.MCTSPlayer(qz.mcts.DeviceStub("S3"), c_puct=5, n_playout=24, is_selfplay=1)
+    move, probs = player.choose_action(g, temp=1.0, return_prob=1)
+    assert move in g.actions() and probs.shape == (140,) and abs(probs.sum() - 1.0) < 1e-9
+    assert player.get_action(g, temp=1.0) in g.actions()
+    player.reset_player()
+    # a short self-play game from a late position is too long to reach with random S3; run the real loop
+    # with a pawn-only endgame by monkey-patching reset
+    def late_reset(self=g):
+        qz.q.Quoridor.reset(self)
+        self._positions = {1: 58, 2: 22}
+        self._player1_walls_remaining = self._player2_walls_remaining = 0
+    g.reset = late_reset
+    fast = qz.mcts.MCTSPlayer(qz.mcts.DeviceStub("S3"), c_puct=5, n_playout=30, is_selfplay=1, fix_terminal_sign=True)
+    winner, data = g.start_self_play(fast, temp=1.0)
+    data = list(data)
+    assert winner in (1, 2) and len(data) >= 2
+    s, p, z = data[0]
+    assert s.shape == (26, 9, 9) and p.shape == (140,) and z in (-1.0, 1.0)
+    zs = [d[2] for d in data]
+    assert zs[-1] == 1.0                                         # the last mover won
+    pure = qz.pure.MCTSPlayer(c_puct=5, n_playout=40)
+    h = qz.q.Quoridor()
+    mv = pure.choose_action(h)
+    assert mv in h.actions()
