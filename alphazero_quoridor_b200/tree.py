@@ -211,7 +211,9 @@ class BatchedMCTS:
         total = self.n_playout if n_playout is None else int(n_playout)
         done = 0
         while done < total:
-            k = min(self.K, total - done)
+            # the first playout after a reset/advance may find an unexpanded root: K descents would all
+            # stop there, so that wave collects a single leaf per game
+            k = 1 if self.playouts_done == 0 else min(self.K, total - done)
             self.playout_wave(k)
             done += k
 
