@@ -68,7 +68,12 @@ def load():
     return lib
 
 
+LAUNCHES = 0      # kernels of ours launched through the C ABI (bench.py reports it as gpu_launches)
+
+
 def check(rc, what=""):
+    global LAUNCHES
+    LAUNCHES += 1
     if rc != 0:
         msg = load().qz_last_error_string().decode("utf-8", "replace")
         raise QzError("%s failed with code %d: %s" % (what or "libqzb200 call", rc, msg))

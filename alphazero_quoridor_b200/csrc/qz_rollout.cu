@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(128) qz_rollout_kernel(QzRolloutArgs a) {
     QzRng rng;
     int64_t r = -1;        // rollout this lane is running, -1 = none
     int player0 = 0, steps = 0;
+    unsigned long long my_plies = 0;
     bool exhausted = false;
     s.H = s.V = s.meta = 0;
     rng = qz_rng_init(0, 0);
@@ -71,10 +72,15 @@ __global__ void __launch_bounds__(128) qz_rollout_kernel(QzRolloutArgs a) {
                 a.result[r] = (int8_t)(winner == 0 ? 0 : (winner == player0 ? 1 : -1));     // :104-108
                 if (a.plies) a.plies[r] = steps;
                 if (a.final_states) qz_store_state(a.final_states + r, s);
+                my_plies += (unsigned long long)steps;
                 r = -1;
             }
         }
     }
+    // cumulative env-step counter (workspace[1]; never zeroed by the library)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) my_plies += __shfl_xor_sync(QZ_FULL_MASK, my_plies, off);
+    if (lane == 0 && my_plies) atomicAdd(a.counter + 1, my_plies);
 }
 
 extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,

@@ -1,0 +1,109 @@
+"""Batched self-play: thousands of concurrent `Quoridor.start_self_play` loops (quoridor.py:573-610) driven by
+`tree.BatchedMCTS`, i.e. the batched form of `TrainPipeline.collect_selfplay_data` (train.py:55-63).
+
+One `step()` = one ply for every game: search (n_playout playouts per game), pick a move
+(mcts.py:177-187 / pure_mcts.py:115), optionally record (state, move probabilities, mover), play the move and
+re-root (mcts.py:146-151); games that end are scored, handed to the replay sink and restarted from `reset()`.
+
+Games are identified by a GLOBAL game index (`game_id_base + i`), which keys every random stream, so a set of
+games gives the same results however it is sharded over GPUs (no collective on this path).
+"""
+import torch
+
+from .quoridor import BatchedQuoridor
+from .tree import BatchedMCTS, RolloutEvaluator
+
+
+class BatchedSelfPlay:
+    def __init__(self, n_games, evaluator, c_puct=5, n_playout=400, leaves_per_game=8, temp=1.0, pure=False,
+                 seed=0, game_id_base=0, max_plies=600, record=False, fix_terminal_sign=False, device=None,
+                 node_cap=None):
+        self.pure = bool(pure)
+        self.temp = float(temp)
+        self.seed = int(seed)
+        self.max_plies = int(max_plies)
+        self.record = bool(record)
+        self.mcts = BatchedMCTS(n_games, evaluator, c_puct=c_puct, n_playout=n_playout,
+                                leaves_per_game=leaves_per_game, reuse_tree=not self.pure,
+                                fix_terminal_sign=fix_terminal_sign, device=device, node_cap=node_cap)
+        self.n = self.mcts.n
+        dev = self.device = self.mcts.device
+        self.lib = self.mcts.lib
+        # games per slot so far; RNG stream of slot i's current game = (game_id_base + i) + n_slots_total * games_played
+        self.game_id_base = int(game_id_base)
+        self.games_started = torch.zeros(self.n, dtype=torch.int64, device=dev)
+        self._slot = torch.arange(self.n, dtype=torch.int64, device=dev) + self.game_id_base
+        self.stride = 1 << 24            # rollout/RNG ids: game stream id * stride + playout counter
+        self._start = BatchedQuoridor(1, device=dev).states
+        self.mcts.reset(self._start.expand(self.n, 3).contiguous())
+        self._set_game_ids()
+        self.finished_games = torch.zeros((), dtype=torch.int64, device=dev)
+        self.p1_wins = torch.zeros((), dtype=torch.int64, device=dev)
+        self.truncated_games = torch.zeros((), dtype=torch.int64, device=dev)
+        self.moves_played = 0
+        if self.record:
+            T = self.max_plies
+            self.rec_state = torch.zeros((T, self.n, 3), dtype=torch.int64, device=dev)
+            self.rec_probs = torch.zeros((T, self.n, 140), dtype=torch.float32, device=dev)
+            self.sink = []               # list of (states int64 [m,3], probs f32 [m,140], z f32 [m]) per flush
+
+    def _set_game_ids(self):
+        # a stream id unique per (slot, game-in-slot); shifted so per-playout counters never collide
+        gid = self._slot + self.games_started * (1 << 20)
+        self.mcts.game_id.copy_(gid * self.stride if isinstance(self.mcts.evaluator, RolloutEvaluator) else gid)
+
+    def step(self):
+        m = self.mcts
+        m.search()
+        if self.pure:
+            moves = m.choose(mode=0)
+        else:
+            moves = m.choose(mode=2, temp=self.temp, seed=self.seed)
+        ply = ((m.root_state[:, 2] >> 48) & 0xFFFF)
+        if self.record:
+            _, probs, _ = m.root_stats(temp=self.temp)
+            t = ply.clamp(max=self.max_plies - 1)
+            idx = torch.arange(self.n, device=self.device)
+            self.rec_state[t, idx] = m.root_state
+            self.rec_probs[t, idx] = probs.float()
+        m.advance(moves, keep_subtree=not self.pure)
+        self.moves_played += self.n
+        self._finish_games()
+        return moves
+
+    def _finish_games(self):
+        m = self.mcts
+        meta = m.root_state[:, 2]
+        done = ((meta >> 40) & 1).bool()
+        ply = (meta >> 48) & 0xFFFF
+        trunc = (~done) & (ply >= self.max_plies)
+        over = done | trunc
+        if not bool(over.any()):
+            return
+        winner = (meta >> 41) & 3
+        self.finished_games += over.sum()
+        self.p1_wins += (over & (winner == 1)).sum()
+        self.truncated_games += trunc.sum()
+        if self.record:
+            self._flush(over, winner, ply)
+        sel = over.to(torch.uint8).contiguous()
+        fresh = torch.where(over.unsqueeze(1), self._start.expand(self.n, 3), m.root_state).contiguous()
+        m.reset(fresh, select=sel)            # fresh root + start position for the finished slots only
+        self.games_started += over.to(torch.int64)
+        self._set_game_ids()
+
+    def _flush(self, over, winner, ply):
+        """quoridor.py:596-610: z = +1 on the winner's plies, -1 on the loser's (0 for a truncated game)."""
+        idx = over.nonzero().flatten()
+        for g in idx.tolist():
+            T = int(min(int(ply[g].item()), self.max_plies))
+            if T == 0:
+                continue
+            st = self.rec_state[:T, g].clone()
+            pr = self.rec_probs[:T, g].clone()
+            mover = (st[:, 2] >> 32) & 0xFF
+            w = int(winner[g].item())
+            z = torch.zeros(T, dtype=torch.float32, device=self.device)
+            if w:
+                z = torch.where(mover == w, torch.ones_like(z), -torch.ones_like(z))
+            self.sink.append((st, pr, z))

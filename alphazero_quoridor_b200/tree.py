@@ -144,6 +144,8 @@ class BatchedMCTS:
         self.game_id = torch.arange(self.n, dtype=torch.int64, device=dev)
         self.playouts_done = 0       # playouts since the last reset/advance (per game)
         self.total_playouts = 0
+        self.count_tree_steps = False    # bench: accumulate the env steps replayed by the descents
+        self.tree_steps = torch.zeros((), dtype=torch.int64, device=dev)
         self._structs = [self._make_struct(a) for a in self.arenas]
 
     # ---- plumbing ----
@@ -192,6 +194,8 @@ class BatchedMCTS:
             _lib.check(self.lib.qz_mcts_select(C.byref(self.tree), self.c_puct, int(self.uniform_prior), k, st),
                        "qz_mcts_select")
             m = self.n * self.K
+            if self.count_tree_steps:
+                self.tree_steps += (self.path_len.clamp(min=1) - 1).sum()
             _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(self.leaf_state), _lib.ptr(self.leaf_mask), m, st),
                        "qz_env_legal_mask")
             # rollout / RNG stream of leaf (g,k): unique per (game, playout)

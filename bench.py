@@ -1,0 +1,400 @@
+#!/usr/bin/env python3
+"""Contract benchmark (one JSON line on stdout, rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            # ours
+    python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1]): pure-MCTS self-play, 1000 random rollouts per move, c_puct 5, 4096
+concurrent games PER GPU (weak scaling; games are sharded by global game index, no collective on the hot
+path).  One "step" = one ply of self-play for every game: 1000 playouts per game (descent, leaf legality sweep,
+expansion, a random rollout of <= 999 plies, backup), first-max-visits move, env step, finished games restart.
+Metric: env steps per second (tree-descent steps + rollout plies + the moves played), whole job.
+
+The reference arm times the CPU oracle's port of the same path (oracle/quoridor_oracle.c: pure_mcts.py:66-115
+on top of the literal quoridor.py rules) on all host cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "env_steps_per_s"
+UNIT = "env steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--playouts", type=int, default=1000)
+    ap.add_argument("--leaves", type=int, default=64, help="leaves per game per wave (virtual loss)")
+    ap.add_argument("--c-puct", type=float, default=5.0)
+    ap.add_argument("--seed", type=int, default=20261017)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline micro-section")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return "pure_mcts selfplay: %d rollouts/move, %d concurrent games/GPU, c_puct %g, rollout limit 1000" % (
+        a.playouts, a.games, a.c_puct)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_pure_mcts_sample(args, target_s, threads=0):
+    """The oracle's port of pure_mcts.py timed on the host cores: G start-position games x P playouts with a
+    fresh tree each, the reference's algorithm restated literally (full 128-candidate sweep per expansion AND per
+    rollout ply, BFS path checks).  Returns the cpu_baseline dict."""
+    import numpy as np
+    from oracle import oracle as O
+    cores = O.max_threads() if threads <= 0 else threads
+    H = np.zeros(1, dtype=np.uint64)
+    V = np.zeros(1, dtype=np.uint64)
+    meta = np.array([[4, 76, 10, 10, 1]], dtype=np.int32)
+    # probe: one game per core, 4 playouts
+    g0 = max(cores, 1)
+    t0 = time.perf_counter()
+    steps, playouts, _ = O.pure_mcts_moves(np.repeat(H, g0), np.repeat(V, g0), np.repeat(meta, g0, 0), 4,
+                                           c_puct=args.c_puct, seed=args.seed, threads=cores, literal_rollouts=True)
+    dt = max(time.perf_counter() - t0, 1e-3)
+    per_playout = dt * cores / max(playouts, 1)          # core-seconds per playout
+    want_playouts = max(int(target_s * cores / per_playout), cores * 8)
+    p = max(8, min(args.playouts, want_playouts // (2 * cores)))
+    g = max(cores, min(args.games, want_playouts // p))
+    t0 = time.perf_counter()
+    steps, playouts, _ = O.pure_mcts_moves(np.repeat(H, g), np.repeat(V, g), np.repeat(meta, g, 0), p,
+                                           c_puct=args.c_puct, seed=args.seed + 1, threads=cores, literal_rollouts=True)
+    dt = time.perf_counter() - t0
+    # for context: the same port with the product's sampled-legality rollout (one path check per wall ply)
+    t1 = time.perf_counter()
+    s2, _, _ = O.pure_mcts_moves(np.repeat(H, g), np.repeat(V, g), np.repeat(meta, g, 0), p,
+                                 c_puct=args.c_puct, seed=args.seed + 1, threads=cores, literal_rollouts=False)
+    dt2 = time.perf_counter() - t1
+    info = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%d start-position games x %d playouts (fresh tree each), %.1f s on %d host threads; "
+                      "oracle/quoridor_oracle.c: literal quoridor.py rules + pure_mcts.py:66-115, one full actions() "
+                      "sweep per rollout ply (the reference's 2 further recomputations per ply, quoridor.py:165 and "
+                      "pure_mcts.py:9-10, are not repeated)" % (g, p, dt, cores),
+            "playouts_per_s": playouts / dt, "seconds": dt,
+            "port_with_sampled_legality": {"value": s2 / dt2, "unit": UNIT,
+                                           "note": "same port, rollout plies verify only the drawn wall (the product's algorithm)"}}
+    return info
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals, last = [], None
+    for i in range(args.warmup + args.steps):
+        info = cpu_pure_mcts_sample(args, target_s=max(2.0, min(args.cpu_seconds, 60.0 / max(args.steps + args.warmup, 1))))
+        if i >= args.warmup:
+            vals.append(info)
+        last = info
+    steps_total = sum(v["value"] * v["seconds"] for v in vals)
+    secs = sum(v["seconds"] for v in vals)
+    value = steps_total / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(len(vals), 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "parallelism": "host threads"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": "port", "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from alphazero_quoridor_b200 import _lib
+    from alphazero_quoridor_b200.selfplay import BatchedSelfPlay
+    from alphazero_quoridor_b200.tree import RolloutEvaluator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+
+    ev = RolloutEvaluator(seed=args.seed, limit=1000)
+    sp = BatchedSelfPlay(args.games, ev, c_puct=args.c_puct, n_playout=args.playouts, leaves_per_game=args.leaves,
+                         pure=True, seed=args.seed, game_id_base=rank * args.games, device=dev)
+    m = sp.mcts
+    m.count_tree_steps = True
+    ws = torch.zeros(2, dtype=torch.int64, device=dev)       # [0] work counter, [1] cumulative rollout plies
+    ev._ws = ws
+    # time every rollout launch on its stream (roofline of the dominant kernel)
+    roll_events = []
+    orig_eval = ev.evaluate
+
+    def timed_eval(mcts, leaf_states, masks, rids):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        out = orig_eval(mcts, leaf_states, masks, rids)
+        b.record()
+        roll_events.append((a, b, leaf_states.shape[0]))
+        return out
+    ev.evaluate = timed_eval
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        sp.step()
+    barrier()
+    roll_events.clear()
+    ws[1] = 0
+    m.tree_steps.zero_()
+    moves0 = sp.moves_played
+    launches0 = _lib.LAUNCHES
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        sp.step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clk = clocks.stop() if rank == 0 else None
+    launches = _lib.LAUNCHES - launches0
+    env_steps = int(ws[1].item()) + int(m.tree_steps.item()) + (sp.moves_played - moves0)
+    playouts = args.games * args.playouts * args.steps
+    roll_ms = [a.elapsed_time(b) for a, b, _ in roll_events]
+    roll_n = [n for _, _, n in roll_events]
+    stats = torch.tensor([ms, float(env_steps), float(playouts), float(sum(roll_ms)), float(launches)],
+                         dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms, env_total, playouts_total = mx[0].item(), sm[1].item(), sm[2].item()
+    else:
+        env_total, playouts_total = float(env_steps), float(playouts)
+
+    # ---- end to end through the C ABI with HOST buffers: states H2D, search, moves/visits/new states D2H ----
+    host_states = torch.empty((args.games, 3), dtype=torch.int64).pin_memory()
+    host_moves = torch.empty((args.games,), dtype=torch.int32).pin_memory()
+    host_visits = torch.empty((args.games, 140), dtype=torch.int32).pin_memory()
+    host_states.copy_(m.root_state)
+    torch.cuda.synchronize()
+    ws[1] = 0
+    m.tree_steps.zero_()
+    e2e_steps = max(1, min(args.steps, 2))
+    barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(e2e_steps):
+        dstates = host_states.to(dev, non_blocking=True)
+        m.reset(dstates)
+        m.search()
+        visits, _, _ = m.root_stats(temp=1.0)
+        moves = m.choose(mode=0)
+        m.advance(moves, keep_subtree=False)
+        host_moves.copy_(moves, non_blocking=True)
+        host_visits.copy_(visits, non_blocking=True)
+        host_states.copy_(m.root_state, non_blocking=True)
+        torch.cuda.synchronize()
+        # finished games restart on the host side of the boundary
+        done = ((host_states[:, 2] >> 40) & 1).bool()
+        if bool(done.any()):
+            host_states[done] = sp._start.cpu()[0]
+    t1.record()
+    barrier()
+    e2e_ms = t0.elapsed_time(t1)
+    e2e_env = int(ws[1].item()) + int(m.tree_steps.item()) + args.games * e2e_steps
+    e2e_stats = torch.tensor([e2e_ms, float(e2e_env)], dtype=torch.float64, device=dev)
+    if world > 1:
+        a = e2e_stats.clone()
+        dist.all_reduce(a, op=dist.ReduceOp.MAX)
+        b = e2e_stats.clone()
+        dist.all_reduce(b, op=dist.ReduceOp.SUM)
+        e2e_ms, e2e_env = a[0].item(), b[1].item()
+    h2d = args.games * 24
+    d2h = args.games * (4 + 140 * 4 + 24)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (qz_rollout_kernel): algorithmic HBM bytes per launch / its duration ----
+    # per rollout: 24 B start state + 4 B state index + 8 B stream id read, 1 B result written  
+    bytes_per_rollout = 24 + 4 + 8 + 1
+    avg_ms = sum(roll_ms) / max(len(roll_ms), 1)
+    avg_n = sum(roll_n) / max(len(roll_n), 1)
+    achieved = bytes_per_rollout * avg_n / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
+    roofline = {"kernel": "qz_rollout_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "launches_timed": len(roll_ms), "avg_launch_ms": avg_ms, "rollouts_per_launch": avg_n,
+                "share_of_step": sum(roll_ms) / ms if ms > 0 else None,
+                "note": "the rollout keeps the whole game in registers; it is instruction-issue bound, not HBM "
+                        "bound (SURVEY.md 8d), so frac against the HBM peak is tiny by design -- see issue_model and "
+                        "profiles/ for warp-issue efficiency; HBM-bound kernels are listed under `kernels`"}
+    line = {
+        "metric": METRIC, "value": env_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "games_per_gpu": args.games, "playouts_per_move": args.playouts,
+                   "leaves_per_game_per_wave": args.leaves, "parallelism": "games sharded by index x%d, no collective" % world,
+                   "l2": "inputs larger than L2: tree arenas %.1f GB/GPU; rollouts are register resident" % (m.nbytes() / 1e9)},
+        "mcts_sims_per_s": playouts_total / (ms * 1e-3),
+        "moves_per_s": args.games * world * args.steps / (ms * 1e-3),
+        "env_steps_per_playout": env_total / playouts_total,
+        "clocks": clk,
+        "e2e": {"value": e2e_env / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+    }
+    if not args.no_kernels:
+        try:
+            line["kernels"] = kernel_section(torch, dev, hbm_peak)
+        except Exception as ex:  # the headline must survive a failure of the side section
+            line["kernels"] = {"error": repr(ex)}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_pure_mcts_sample(args, args.cpu_seconds)
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_section(torch, dev, hbm_peak):
+    """Live CUDA-event timings of the other kernels on the path with their algorithmic bytes."""
+    from alphazero_quoridor_b200.quoridor import BatchedQuoridor
+    from alphazero_quoridor_b200.synthetic import midgame_positions
+
+    def timed(fn, iters=5, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    out = {}
+    n = 1 << 20
+    states = midgame_positions(n, seed=7, device=dev)
+    env = BatchedQuoridor(n, states=states, device=dev)
+    mask = torch.empty((n, 3), dtype=torch.int64, device=dev)
+    ms = timed(lambda: env.legal_mask(out=mask))
+    out["qz_legal_mask_kernel"] = {"units": n, "ms": ms, "sweeps_per_s": n / ms * 1e3, "bytes_per_unit": 48,
+                                   "achieved_GBps": n * 48 / ms / 1e6, "frac_hbm": n * 48 / ms / 1e6 / hbm_peak,
+                                   "bound": "issue (2 flood fills per candidate)",
+                                   "workload": "BASELINE config 5: 2^20 positions, 10-20 plies of random play"}
+    n2 = 1 << 19     # 2.2 GB of bf16 planes: larger than L2
+    env2 = BatchedQuoridor(n2, states=states[:n2].clone(), device=dev)
+    for dt, name in ((torch.bfloat16, "bf16"), (torch.float32, "f32")):
+        buf = torch.empty((n2, 26, 9, 9), dtype=dt, device=dev)
+        ms = timed(lambda: env2.encode(out=buf))
+        nb = buf.numel() * buf.element_size() + n2 * 24
+        out["qz_encode_kernel_" + name] = {"units": n2, "ms": ms, "bytes_per_unit": nb // n2,
+                                           "achieved_GBps": nb / ms / 1e6, "frac_hbm": nb / ms / 1e6 / hbm_peak, "bound": "hbm"}
+        del buf
+    n3 = 1 << 24     # 403 MB of states: larger than L2
+    env3 = BatchedQuoridor(n3, device=dev)
+    acts = torch.full((n3,), 2, dtype=torch.int32, device=dev)       # E then (opponent) E ... never terminal
+    done = torch.empty(n3, dtype=torch.uint8, device=dev)
+    ms = timed(lambda: env3.step(acts, done=done), iters=4, warm=2)
+    nb = n3 * (24 + 4 + 24 + 1)
+    out["qz_step_kernel"] = {"units": n3, "ms": ms, "bytes_per_unit": 53, "achieved_GBps": nb / ms / 1e6,
+                             "frac_hbm": nb / ms / 1e6 / hbm_peak, "bound": "hbm", "steps_per_s": n3 / ms * 1e3}
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -119,7 +119,9 @@ int qz_env_encode(const qz_state *states, void *out, int dtype, int layout, int 
  *   limit                the reference's `limit` (1000): at most limit-1 plies are played.
  *   result[r]            +1 / -1 from the STARTING mover's point of view, 0 if nobody won (:104-108).
  *   plies[r]             (nullable) plies played.     final_states[r]  (nullable) where the rollout ended.
- *   workspace            >= 8 bytes of device scratch, zeroed by the call.
+ *   workspace            >= 16 bytes of device scratch (8-byte aligned): word 0 is the work counter, zeroed by
+ *                        the call; word 1 ACCUMULATES the plies played by every call (caller zeroes / reads it),
+ *                        i.e. the env-step count without a per-rollout reduction.
  */
 int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
                int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,

@@ -78,6 +78,7 @@ def lib():
                                          i32p]
         L.oq_bench_stub_mcts.restype = C.c_longlong
         L.oq_max_threads.restype = C.c_int
+        L.oq_set_literal_rollouts.argtypes = [C.c_int]
         _lib = L
     return _lib
 
@@ -237,8 +238,10 @@ def sweeps(H, V, meta5, threads=0):
     return total, mask
 
 
-def pure_mcts_moves(H, V, meta5, n_playout, c_puct=5.0, seed=0, threads=0):
+def pure_mcts_moves(H, V, meta5, n_playout, c_puct=5.0, seed=0, threads=0, literal_rollouts=False):
+    """literal_rollouts=True: every rollout ply runs the full actions() sweep, as pure_mcts.py:7-10 does."""
     H, V, meta5 = _pos_arrays(H, V, meta5)
+    lib().oq_set_literal_rollouts(int(literal_rollouts))
     moves = np.zeros(len(H), dtype=np.int32)
     playouts = C.c_longlong()
     steps = lib().oq_bench_pure_mcts(_p(H, C.c_uint64), _p(V, C.c_uint64), _p(meta5, C.c_int), len(H), n_playout,

@@ -589,6 +589,32 @@ int oq_rollout(oq_game *game, uint64_t seed, uint64_t rid, int limit, int *plies
     return winner == player ? 1 : -1;
 }
 
+/* pure_mcts.py:86-108 restated LITERALLY: every ply builds the full legal list with actions() (the whole
+ * 128-candidate sweep while the mover has walls) and picks uniformly from it (rollout_policy_fn, :7-10).
+ * This is the form the CPU baseline times; results are distributed exactly like oq_rollout's. */
+int oq_rollout_literal(oq_game *game, uint64_t seed, uint64_t rid, int limit, int *plies) {
+    int player = game->current_player;
+    int winner = 0, steps = 0;
+    for (int i = 0; i < limit; i++) {
+        if (oq_has_a_winner(game, &winner)) break;
+        if (i == limit - 1) break;
+        int acts[140];
+        int n = oq_actions(game, acts);
+        if (n == 0) break;
+        uint32_t w[4];
+        oq_philox(seed, rid, (uint32_t)i >> 2, 0, w);
+        int a = acts[(int)(((uint64_t)w[i & 3] * (uint32_t)n) >> 32)];
+        oq_step(game, a);
+        steps++;
+    }
+    if (plies) *plies = steps;
+    if (winner == 0) return 0;
+    return winner == player ? 1 : -1;
+}
+
+static int oq_literal_rollouts = 0;
+void oq_set_literal_rollouts(int on) { oq_literal_rollouts = on; }
+
 /* pure_mcts.py:66-83 */
 static void pure_playout(oq_mcts *t, oq_game *game) {
     oq_node *node = t->root;
@@ -608,7 +634,9 @@ static void pure_playout(oq_mcts *t, oq_game *game) {
         node_expand(node, acts, pri, n);
     }
     int plies = 0;
-    double leaf_value = (double)oq_rollout(game, t->rng_seed, t->rollout_counter++, 1000, &plies);
+    double leaf_value = oq_literal_rollouts
+        ? (double)oq_rollout_literal(game, t->rng_seed, t->rollout_counter++, 1000, &plies)
+        : (double)oq_rollout(game, t->rng_seed, t->rollout_counter++, 1000, &plies);
     t->env_steps += plies;
     if (end && t->fix_terminal_sign) leaf_value = -leaf_value;
     node_update_recursive(node, -leaf_value);
