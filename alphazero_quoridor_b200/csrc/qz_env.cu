@@ -59,7 +59,7 @@ extern "C" int qz_env_step(qz_state *states, const int32_t *actions, const uint6
 
 // ------------------------------------------------------------------------------------------ legal mask
 // One warp per game (4 games per 128-thread block).
-__global__ void __launch_bounds__(128) qz_legal_mask_kernel(const qz_state *__restrict__ states,
+__global__ void __launch_bounds__(128, 4) qz_legal_mask_kernel(const qz_state *__restrict__ states,
                                                             uint64_t *__restrict__ mask3, int64_t n) {
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n) return;

@@ -312,43 +312,112 @@ QZ_HD int qz_delta(int a) {
     return a < 8 ? (int)(int8_t)(lo >> (8 * a)) : (int)(int8_t)(hi >> (8 * (a - 8)));
 }
 
+// ---- branch-free pawn-move generation from per-corner masks ---------------------------------------------------
+// The scalar qz_corners/qz_pawn_moves above mirror the reference line by line but branch on the tile, which
+// serialises a warp whose lanes stand on different tiles.  The device paths therefore use twelve 81-bit masks
+// built once per wall configuration: for every tile, "corner k IS a horizontal / vertical wall" (synthetic
+// border walls and the row-0 NE/NW aliasing included, quoridor.py:356-418) and the four plain-move masks
+// derived from them.  A pawn-move query is then ~20 bit tests and no branch (quoridor.py:272-353).
+struct QzPawnCtx {
+    QzDirs d;
+    BB neV, nwV, seV, swV;
+    BB neH, nwH, seH, swH;
+};
+
+QZ_HD BB bb_make(uint32_t w0, uint32_t w1, uint32_t w2) { BB b; b.w0 = w0; b.w1 = w1; b.w2 = w2; return b; }
+QZ_HD uint32_t bb_at(const BB &b, int t) {     // bit t as 0/1, 0 <= t <= 80
+    const uint32_t w = t < 32 ? b.w0 : (t < 64 ? b.w1 : b.w2);
+    return (w >> (t & 31)) & 1u;
+}
+
+QZ_HD QzPawnCtx qz_ctx_build(uint64_t H, uint64_t V) {
+    const BB h9 = bb_spread8(H), v9 = bb_spread8(V);
+    const uint32_t r0h = h9.w0 & 0xFFu, r0v = v9.w0 & 0xFFu;
+    const uint32_t fixh = (r0h << 1) | (r0h & 1u), fixv = (r0v << 1) | (r0v & 1u);   // row 0: NE = NW = ix(0,c-1)
+    QzPawnCtx c;
+    c.neV = bb_or(v9, bb_make(0x04020000u, QZ_COL8_W1, 0x80u));        // column 8, rows 1..7
+    c.neV.w0 = (c.neV.w0 & ~QZ_ROW0_W0) | fixv;
+    c.neH = h9;
+    c.neH.w2 |= QZ_ROW8_W2;                                             // row 8: NE = H
+    c.neH.w0 = (c.neH.w0 & ~QZ_ROW0_W0) | fixh;
+    c.nwV = bb_or(bb_shl(v9, 1), bb_make(QZ_COL0_W0, QZ_COL0_W1, QZ_COL0_W2));
+    c.nwH = bb_shl(h9, 1);
+    c.nwH.w2 |= 0x1FE00u;                                               // row 8, columns 1..8
+    c.seV = bb_or(bb_shl(v9, 9), bb_make(QZ_COL8_W0, QZ_COL8_W1, QZ_COL8_W2));
+    c.seH = bb_shl(h9, 9);
+    c.seH.w0 |= 0xFFu;                                                  // row 0, columns 0..7
+    c.swV = bb_or(bb_shl(v9, 10), bb_make(0x08040200u, QZ_COL0_W1, QZ_COL0_W2));   // column 0, rows 1..8
+    c.swH = bb_shl(h9, 10);
+    c.swH.w0 |= QZ_ROW0_W0;                                             // row 0
+    c.d.n.w0 = ~(c.nwH.w0 | c.neH.w0); c.d.n.w1 = ~(c.nwH.w1 | c.neH.w1); c.d.n.w2 = ~(c.nwH.w2 | c.neH.w2) & QZ_BOARD_W2;
+    c.d.s.w0 = ~(c.swH.w0 | c.seH.w0); c.d.s.w1 = ~(c.swH.w1 | c.seH.w1); c.d.s.w2 = ~(c.swH.w2 | c.seH.w2) & QZ_BOARD_W2;
+    c.d.e.w0 = ~(c.neV.w0 | c.seV.w0); c.d.e.w1 = ~(c.neV.w1 | c.seV.w1); c.d.e.w2 = ~(c.neV.w2 | c.seV.w2) & QZ_BOARD_W2;
+    c.d.w.w0 = ~(c.nwV.w0 | c.swV.w0); c.d.w.w1 = ~(c.nwV.w1 | c.swV.w1); c.d.w.w2 = ~(c.nwV.w2 | c.swV.w2) & QZ_BOARD_W2;
+    return c;
+}
+
+// quoridor.py:272-353 without a branch.  L on the board; any O (an off-board O is never adjacent).
+QZ_HD uint32_t qz_pawn_moves_ctx(const QzPawnCtx &c, int L, int O, int player) {
+    const uint32_t ovalid = (unsigned)O <= 80u ? 1u : 0u;
+    const int Oc = ovalid ? O : 0;
+    const uint32_t p1 = player == 1 ? 1u : 0u, p2 = p1 ^ 1u;
+    const uint32_t on = (L == O - 9 ? 1u : 0u) & ovalid, os = (L == O + 9 ? 1u : 0u) & ovalid;
+    const uint32_t oe = (L == O - 1 ? 1u : 0u) & ovalid, ow = (L == O + 1 ? 1u : 0u) & ovalid;
+    const uint32_t nL = bb_at(c.d.n, L), sL = bb_at(c.d.s, L), eL = bb_at(c.d.e, L), wL = bb_at(c.d.w, L);
+    uint32_t m = ((nL & (on ^ 1u)) | (p1 & (L >= 72 ? 1u : 0u)))
+               | (((sL & (os ^ 1u)) | (p2 & (L < 9 ? 1u : 0u))) << 1)
+               | ((eL & (oe ^ 1u)) << 2) | ((wL & (ow ^ 1u)) << 3);
+    const uint32_t gN = on & nL, gS = os & sL, gE = oe & eL, gW = ow & wL;      // wall-free contact with the opponent
+    const uint32_t nn = gN & (bb_at(c.d.n, Oc) | (p1 & (L >= 63 ? 1u : 0u)));   // :305-308 (row 7, P1: off-board win)
+    const uint32_t ss = gS & (bb_at(c.d.s, Oc) | (p2 & (L < 18 ? 1u : 0u)));    // :319-321 (row 1, P2)
+    const uint32_t ee = gE & bb_at(c.d.e, Oc);
+    const uint32_t ww = gW & bb_at(c.d.w, Oc);
+    const uint32_t ne = (gN & (bb_at(c.neV, Oc) ^ 1u) & (bb_at(c.neV, L) ^ 1u)) | (gE & (bb_at(c.neH, Oc) ^ 1u));
+    const uint32_t nw = (gN & (bb_at(c.nwV, Oc) ^ 1u) & (bb_at(c.nwV, L) ^ 1u)) | (gW & (bb_at(c.nwH, Oc) ^ 1u));
+    const uint32_t se = (gS & (bb_at(c.seV, Oc) ^ 1u) & (bb_at(c.seV, L) ^ 1u)) | (gE & (bb_at(c.seH, Oc) ^ 1u));
+    const uint32_t sw = (gS & (bb_at(c.swV, Oc) ^ 1u) & (bb_at(c.swV, L) ^ 1u)) | (gW & (bb_at(c.swH, Oc) ^ 1u));
+    m |= (nn << 4) | (ss << 5) | (ee << 6) | (ww << 7) | (ne << 8) | (nw << 9) | (se << 10) | (sw << 11);
+    return m;
+}
+
 // ---- jump edges seen by the path check ------------------------------------------------------------------
 // In _bfs_to_goal (quoridor.py:479-528) the opponent pawn is a fixed obstacle: plain moves into its
 // tile are dropped and up to three jump edges leave each of the four neighbouring tiles.  Encoded as one
 // u32: byte i = actions 4..11 available from source tile O + QZ_SRC[i]  (i: 0 = O-9, 1 = O+9, 2 = O-1, 3 = O+1).
 QZ_HD int qz_jump_src(int O, int i) { return O + (i == 0 ? -9 : (i == 1 ? 9 : (i == 2 ? -1 : 1))); }
 
-QZ_HD_NOINLINE uint32_t qz_jump_set(uint64_t H, uint64_t V, int O, int player) {
+QZ_HD uint32_t qz_jump_set_ctx(const QzPawnCtx &c, int O, int player) {
     uint32_t js = 0;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        int src = qz_jump_src(O, i);
-        if (src < 0 || src > 80) continue;
-        uint32_t m = qz_pawn_moves(H, V, src, O, player) >> 4;
-        js |= (m & 0xFFu) << (8 * i);
+        const int src = qz_jump_src(O, i);
+        const uint32_t valid = (unsigned)src <= 80u ? 1u : 0u;
+        const uint32_t m = qz_pawn_moves_ctx(c, valid ? src : 0, O, player) >> 4;
+        js |= (valid ? (m & 0xFFu) : 0u) << (8 * i);
     }
     return js;
 }
 
-// intersections whose content can change qz_jump_set(.., O, ..): rows r-2..r+1, cols c-2..c+1 of O=(r,c)
-QZ_HD uint64_t qz_jump_near_mask(int O) {
-    int r = O / 9, c = O - 9 * r;
-    int r0 = r - 2 < 0 ? 0 : r - 2, r1 = r + 1 > 7 ? 7 : r + 1;
-    int c0 = c - 2 < 0 ? 0 : c - 2, c1 = c + 1 > 7 ? 7 : c + 1;
-    uint64_t rowbits = ((1ull << (c1 - c0 + 1)) - 1) << c0;
-    uint64_t m = 0;
-    for (int rr = r0; rr <= r1; rr++) m |= rowbits << (8 * rr);
-    return m;
+// Jump edges for one search under an arbitrary wall configuration.  Out of line: only needed when the
+// plain-move closure fails to reach the goal (a blocked or nearly blocked candidate), see qz_reaches_goal.
+QZ_HD_NOINLINE uint32_t qz_jump_set_rebuilt(uint64_t H, uint64_t V, int O, int player) {
+    const QzPawnCtx c = qz_ctx_build(H, V);
+    return qz_jump_set_ctx(c, O, player);
 }
 
 // ---- the path check: can `player` standing on `start` still reach its goal row? -------------------------
 // Same reachability as quoridor.py:479-528: closure of {plain moves not entering O} U {jump edges};
 // touching the goal row ends the search; off-board landings (NN from row 7 / SS from row 1) are recorded by
 // the reference but never expanded and never equal the goal row, so they are dropped here.
-QZ_HD bool qz_reaches_goal(const QzDirs &d, int start, int O, uint32_t jumps, int player) {
+// Jump edges only ADD reachability, so the search first closes over plain moves alone -- which settles almost
+// every legal candidate -- and builds the jump set (walls H, V = the configuration being tested) only if
+// that closure did not touch the goal row.
+QZ_HD bool qz_reaches_goal(const QzDirs &d, int start, int O, int player, uint64_t H, uint64_t V) {
     BB reach = bb_bit(start);
     BB keep = bb_bit(O);
     keep.w0 = ~keep.w0; keep.w1 = ~keep.w1; keep.w2 = ~keep.w2;
+    uint32_t jumps = 0;
+    bool have_jumps = false;
     for (;;) {
         for (;;) {
             BB a = bb_shl(bb_and(reach, d.n), 9);
@@ -363,6 +432,7 @@ QZ_HD bool qz_reaches_goal(const QzDirs &d, int start, int O, uint32_t jumps, in
             if (bb_eq(nxt, reach)) break;
             reach = nxt;
         }
+        if (!have_jumps) { jumps = qz_jump_set_rebuilt(H, V, O, player); have_jumps = true; }
         if (jumps == 0) return false;
         BB add = bb_zero();
 #pragma unroll
@@ -398,18 +468,18 @@ struct QzSweep {
     uint64_t H, V;
     QzDirs dirs;
     int p1, p2;
-    uint32_t j1, j2;        // jump sets seen by P1's search (obstacle P2) and P2's search (obstacle P1)
-    uint64_t near1, near2;  // intersections that can change j1 / j2
 };
 
+QZ_HD QzSweep qz_sweep_prepare_ctx(const QzPawnCtx &c, uint64_t H, uint64_t V, int p1, int p2) {
+    QzSweep w;
+    w.H = H; w.V = V; w.p1 = p1; w.p2 = p2;
+    w.dirs = c.d;
+    return w;
+}
 QZ_HD QzSweep qz_sweep_prepare(uint64_t H, uint64_t V, int p1, int p2) {
     QzSweep w;
     w.H = H; w.V = V; w.p1 = p1; w.p2 = p2;
     w.dirs = qz_dirs(H, V);
-    w.j1 = qz_jump_set(H, V, p2, 1);
-    w.j2 = qz_jump_set(H, V, p1, 2);
-    w.near1 = qz_jump_near_mask(p2);
-    w.near2 = qz_jump_near_mask(p1);
     return w;
 }
 
@@ -420,10 +490,8 @@ QZ_HD bool qz_wall_keeps_paths(const QzSweep &w, int ix, bool vertical) {
     uint64_t bit = 1ull << ix;
     if (vertical) { qz_dirs_place_v(d, ix); V |= bit; }
     else { qz_dirs_place_h(d, ix); H |= bit; }
-    uint32_t j1 = (w.near1 & bit) ? qz_jump_set(H, V, w.p2, 1) : w.j1;
-    if (!qz_reaches_goal(d, w.p1, w.p2, j1, 1)) return false;
-    uint32_t j2 = (w.near2 & bit) ? qz_jump_set(H, V, w.p1, 2) : w.j2;
-    return qz_reaches_goal(d, w.p2, w.p1, j2, 2);
+    if (!qz_reaches_goal(d, w.p1, w.p2, 1, H, V)) return false;
+    return qz_reaches_goal(d, w.p2, w.p1, 2, H, V);
 }
 
 // ---- step (quoridor.py:159-186, :193-202, :217-269) ---------------------------------------------------------
@@ -457,11 +525,15 @@ QZ_HD bool qz_on_board(uint64_t m) {
 }
 
 // pawn part of actions() for the mover (quoridor.py:146)
+QZ_HD uint32_t qz_mover_pawn_moves_ctx(const QzPawnCtx &c, uint64_t meta) {
+    const int cur = qz_cur(meta);
+    const int L = cur == 1 ? qz_p1(meta) : qz_p2(meta);
+    const int O = cur == 1 ? qz_p2(meta) : qz_p1(meta);
+    return qz_pawn_moves_ctx(c, L, O, cur);
+}
 QZ_HD uint32_t qz_mover_pawn_moves(const QzState &s) {
-    int cur = qz_cur(s.meta);
-    int L = cur == 1 ? qz_p1(s.meta) : qz_p2(s.meta);
-    int O = cur == 1 ? qz_p2(s.meta) : qz_p1(s.meta);
-    return qz_pawn_moves(s.H, s.V, L, O, cur);
+    const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+    return qz_mover_pawn_moves_ctx(c, s.meta);
 }
 QZ_HD int qz_mover_walls(uint64_t m) { return qz_cur(m) == 1 ? qz_w1(m) : qz_w2(m); }
 
@@ -477,10 +549,11 @@ QZ_HD void qz_pack_mask(uint32_t pawn, uint64_t hl, uint64_t vl, uint64_t out[3]
 QZ_HD void qz_legal_mask_seq(const QzState &s, uint64_t out[3]) {
     out[0] = out[1] = out[2] = 0;
     if (qz_done(s.meta) || !qz_on_board(s.meta)) return;
-    uint32_t pawn = qz_mover_pawn_moves(s);
+    const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+    uint32_t pawn = qz_mover_pawn_moves_ctx(c, s.meta);
     uint64_t hl = 0, vl = 0;
     if (qz_mover_walls(s.meta) > 0) {
-        QzSweep w = qz_sweep_prepare(s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
+        QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
         uint64_t hc = qz_hcand(s.H, s.V), vc = qz_vcand(s.H, s.V);
         for (int ix = 0; ix < 64; ix++) {
             if (((hc >> ix) & 1) && qz_wall_keeps_paths(w, ix, false)) hl |= 1ull << ix;

@@ -31,9 +31,11 @@ QZ_HD uint32_t qz_rng_first_word(QzRng &r, uint32_t ply) {
     return qz_philox_word(r.blk, (int)(ply & 3u));
 }
 
-// Returns the action (0..139) or -1 when the mover has no legal action (stalemate).
-QZ_HD int qz_sample_action(const QzState &s, QzRng &rng, uint32_t ply) {
-    uint32_t pmask = qz_mover_pawn_moves(s);
+// Returns the action (0..139) or -1 when the mover has no legal action (stalemate); -2 when more than
+// `max_rejects` drawn walls failed the path check (nothing is consumed: the caller redoes the ply another way).
+QZ_HD int qz_sample_action_capped(const QzState &s, QzRng &rng, uint32_t ply, uint32_t max_rejects) {
+    const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+    uint32_t pmask = qz_mover_pawn_moves_ctx(c, s.meta);
     uint64_t hc = 0, vc = 0;
     const bool walls = qz_mover_walls(s.meta) > 0;
     if (walls) { hc = qz_hcand(s.H, s.V); vc = qz_vcand(s.H, s.V); }
@@ -47,7 +49,7 @@ QZ_HD int qz_sample_action(const QzState &s, QzRng &rng, uint32_t ply) {
         int k = (int)qz_mulhi32(word, M);
         if (k < npawn) return qz_nth_bit64((uint64_t)pmask, k);
         k -= npawn;
-        if (!prepared) { w = qz_sweep_prepare(s.H, s.V, qz_p1(s.meta), qz_p2(s.meta)); prepared = true; }
+        if (!prepared) { w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta)); prepared = true; }
         if (k < nh) {
             const int ix = qz_nth_bit64(hc, k);
             if (qz_wall_keeps_paths(w, ix, false)) return 12 + ix;
@@ -55,6 +57,36 @@ QZ_HD int qz_sample_action(const QzState &s, QzRng &rng, uint32_t ply) {
         } else {
             const int ix = qz_nth_bit64(vc, k - nh);
             if (qz_wall_keeps_paths(w, ix, true)) return 76 + ix;
+            vc &= ~(1ull << ix);
+        }
+        if (j >= max_rejects) return -2;
+    }
+}
+
+QZ_HD int qz_sample_action(const QzState &s, QzRng &rng, uint32_t ply) {
+    return qz_sample_action_capped(s, rng, ply, 0xFFFFFFFFu);
+}
+
+// The same draw sequence as qz_sample_action when the legal walls (hl, vl) are already known (from a full
+// sweep): rejected candidates are struck out by table lookup instead of by flood fills.  Identical result.
+QZ_HD int qz_sample_action_known(const QzState &s, QzRng &rng, uint32_t ply, uint32_t pmask, uint64_t hl, uint64_t vl) {
+    uint64_t hc = 0, vc = 0;
+    if (qz_mover_walls(s.meta) > 0) { hc = qz_hcand(s.H, s.V); vc = qz_vcand(s.H, s.V); }
+    for (uint32_t j = 0;; j++) {
+        const int npawn = qz_popc32(pmask), nh = qz_popc64(hc), nv = qz_popc64(vc);
+        const uint32_t M = (uint32_t)(npawn + nh + nv);
+        if (M == 0) return -1;
+        const uint32_t word = j == 0 ? qz_rng_first_word(rng, ply) : qz_philox(rng.seed, rng.rid, ply, j).x;
+        int k = (int)qz_mulhi32(word, M);
+        if (k < npawn) return qz_nth_bit64((uint64_t)pmask, k);
+        k -= npawn;
+        if (k < nh) {
+            const int ix = qz_nth_bit64(hc, k);
+            if ((hl >> ix) & 1ull) return 12 + ix;
+            hc &= ~(1ull << ix);
+        } else {
+            const int ix = qz_nth_bit64(vc, k - nh);
+            if ((vl >> ix) & 1ull) return 76 + ix;
             vc &= ~(1ull << ix);
         }
     }

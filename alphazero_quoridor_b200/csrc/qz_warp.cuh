@@ -17,10 +17,11 @@ __device__ __forceinline__ uint64_t qz_warp_or64(uint64_t x) {
 __device__ __forceinline__ void qz_warp_legal(const QzState &s, uint32_t &pawn, uint64_t &hl, uint64_t &vl) {
     pawn = 0; hl = 0; vl = 0;
     if (qz_done(s.meta) || !qz_on_board(s.meta)) return;
-    pawn = qz_mover_pawn_moves(s);
+    const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+    pawn = qz_mover_pawn_moves_ctx(c, s.meta);
     if (qz_mover_walls(s.meta) <= 0) return;
     const int lane = threadIdx.x & 31;
-    QzSweep w = qz_sweep_prepare(s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
+    const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
     const uint64_t hc = qz_hcand(s.H, s.V), vc = qz_vcand(s.H, s.V);
     const int nh = qz_popc64(hc), total = nh + qz_popc64(vc);
     uint64_t myh = 0, myv = 0;

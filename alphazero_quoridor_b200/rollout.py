@@ -7,6 +7,11 @@ import torch
 from . import _lib
 
 
+def workspace_words(n_rollouts):
+    """int64 words of scratch `rollout` needs for n_rollouts (word 1 accumulates the plies played)."""
+    return (_lib.load().qz_rollout_workspace_bytes(int(n_rollouts)) + 7) // 8
+
+
 def rollout(states, per_state=1, seed=0, rid_base=0, rids=None, state_index=None, limit=1000,
             return_plies=True, return_final=False, workspace=None):
     """Run uniform-random playouts of at most limit-1 plies.
@@ -33,8 +38,10 @@ def rollout(states, per_state=1, seed=0, rid_base=0, rids=None, state_index=None
     result = torch.empty((n_roll,), dtype=torch.int8, device=dev)
     plies = torch.empty((n_roll,), dtype=torch.int32, device=dev) if return_plies else None
     final = torch.empty((n_roll, 3), dtype=torch.int64, device=dev) if return_final else None
+    need = (lib.qz_rollout_workspace_bytes(n_roll) + 7) // 8
     if workspace is None:
-        workspace = torch.empty((2,), dtype=torch.int64, device=dev)
+        workspace = torch.zeros((need,), dtype=torch.int64, device=dev)
+    assert workspace.dtype == torch.int64 and workspace.numel() >= need, "workspace too small: see workspace_words()"
     with torch.cuda.device(dev):
         _lib.check(lib.qz_rollout(_lib.ptr(states.contiguous()), n_states, _lib.ptr(state_index), int(per_state),
                                   n_roll, int(seed) & ((1 << 64) - 1), int(rid_base) & ((1 << 64) - 1),

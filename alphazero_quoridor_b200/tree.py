@@ -83,7 +83,9 @@ class RolloutEvaluator:
 
     def evaluate(self, mcts, leaf_states, masks, leaf_rids):
         if self._ws is None:
-            self._ws = torch.empty((2,), dtype=torch.int64, device=leaf_states.device)
+            from .rollout import workspace_words
+            self._ws = torch.zeros((workspace_words(leaf_states.shape[0]),), dtype=torch.int64,
+                                   device=leaf_states.device)
         res, plies, _ = _rollout(leaf_states, seed=self.seed, rids=leaf_rids,
                                  state_index=mcts._leaf_iota, limit=self.limit,
                                  return_plies=self.count_steps, workspace=self._ws)

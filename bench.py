@@ -197,7 +197,8 @@ def run_ours(args):
                          pure=True, seed=args.seed, game_id_base=rank * args.games, device=dev)
     m = sp.mcts
     m.count_tree_steps = True
-    ws = torch.zeros(2, dtype=torch.int64, device=dev)       # [0] work counter, [1] cumulative rollout plies
+    from alphazero_quoridor_b200.rollout import workspace_words
+    ws = torch.zeros(workspace_words(args.games * args.leaves), dtype=torch.int64, device=dev)   # word 1: cumulative plies
     ev._ws = ws
     # time every rollout launch on its stream (roofline of the dominant kernel)
     roll_events = []

@@ -194,8 +194,12 @@ static int oq_bfs_to_goal(const int8_t *intersections, int target_row, int playe
     return target_visited;
 }
 
+static _Thread_local long long oq_path_checks = 0;   /* statistics for tests / tuning */
+long long oq_get_path_checks(void) { return oq_path_checks; }
+
 /* quoridor.py:463-477 -- both searches always run */
 static int oq_blocks_path(const oq_game *g, int wall_location, int orientation) {
+    oq_path_checks++;
     int8_t ix[64];
     memcpy(ix, g->intersections, 64);
     ix[wall_location] = (int8_t)orientation;

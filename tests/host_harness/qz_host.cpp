@@ -41,6 +41,29 @@ void qh_dirs_incremental(uint64_t H0, uint64_t V0, int ix, int vertical, unsigne
                                    (bb_test(d.w, t) ? 8 : 0));
 }
 
+unsigned qh_pawn_moves_ctx(uint64_t H, uint64_t V, int L, int O, int player) {
+    QzPawnCtx c = qz_ctx_build(H, V);
+    return qz_pawn_moves_ctx(c, L, O, player);
+}
+
+// corner codes of every tile read back from the masks: nw | ne<<2 | se<<4 | sw<<6 (0 none, 1 H, 2 V)
+void qh_ctx_corners(uint64_t H, uint64_t V, unsigned char *out81, unsigned char *scalar81) {
+    QzPawnCtx c = qz_ctx_build(H, V);
+    for (int t = 0; t < 81; t++) {
+        unsigned nw = bb_at(c.nwH, t) | (bb_at(c.nwV, t) << 1), ne = bb_at(c.neH, t) | (bb_at(c.neV, t) << 1);
+        unsigned se = bb_at(c.seH, t) | (bb_at(c.seV, t) << 1), sw = bb_at(c.swH, t) | (bb_at(c.swV, t) << 1);
+        out81[t] = (unsigned char)(nw | (ne << 2) | (se << 4) | (sw << 6));
+        QzCorners k = qz_corners(H, V, t);
+        scalar81[t] = (unsigned char)(k.nw | (k.ne << 2) | (k.se << 4) | (k.sw << 6));
+    }
+}
+
+void qh_dirs_ctx(uint64_t H, uint64_t V, unsigned char *out81) {
+    QzPawnCtx c = qz_ctx_build(H, V);
+    for (int t = 0; t < 81; t++)
+        out81[t] = (unsigned char)(bb_at(c.d.n, t) | (bb_at(c.d.s, t) << 1) | (bb_at(c.d.e, t) << 2) | (bb_at(c.d.w, t) << 3));
+}
+
 void qh_spread8(uint64_t x, uint32_t *w3) { BB b = bb_spread8(x); w3[0] = b.w0; w3[1] = b.w1; w3[2] = b.w2; }
 
 void qh_encode(const uint64_t *s3, float *out) {
@@ -70,6 +93,21 @@ int qh_sample_action(const uint64_t *s3, uint64_t seed, uint64_t rid, uint32_t p
     QzState s{s3[0], s3[1], s3[2]};
     QzRng rng = qz_rng_init(seed, rid);
     return qz_sample_action(s, rng, ply);
+}
+// capped + table-driven sampling must agree with the plain one (-2 = cap hit)
+int qh_sample_action_known(const uint64_t *s3, uint64_t seed, uint64_t rid, uint32_t ply) {
+    QzState s{s3[0], s3[1], s3[2]};
+    uint64_t m[3];
+    qz_legal_mask_seq(s, m);
+    uint32_t pawn; uint64_t hl, vl;
+    qz_unpack_mask(m, pawn, hl, vl);
+    QzRng rng = qz_rng_init(seed, rid);
+    return qz_sample_action_known(s, rng, ply, pawn, hl, vl);
+}
+int qh_sample_action_capped(const uint64_t *s3, uint64_t seed, uint64_t rid, uint32_t ply, uint32_t cap) {
+    QzState s{s3[0], s3[1], s3[2]};
+    QzRng rng = qz_rng_init(seed, rid);
+    return qz_sample_action_capped(s, rng, ply, cap);
 }
 int qh_rollout(uint64_t *s3, uint64_t seed, uint64_t rid, int limit, int *plies) {
     QzState s{s3[0], s3[1], s3[2]};

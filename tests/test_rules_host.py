@@ -143,9 +143,29 @@ def test_direction_masks_match_reference_plain_moves(qh):
         assert inc.raw == full.raw
 
 
+def test_corner_masks_match_scalar_corners(qh):
+    """The branch-free per-corner masks (QzPawnCtx) reproduce quoridor.py:356-418 on every tile."""
+    qh.qh_ctx_corners.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p, C.c_char_p]
+    qh.qh_dirs_ctx.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p]
+    rng = random.Random(12)
+    for it in range(1500):
+        H, V = rand_walls(rng, rng.randrange(0, 34))
+        a, b = C.create_string_buffer(81), C.create_string_buffer(81)
+        qh.qh_ctx_corners(H, V, a, b)
+        assert a.raw == b.raw, (hex(H), hex(V))
+        d1, d2 = C.create_string_buffer(81), C.create_string_buffer(81)
+        qh.qh_dirs_ctx(H, V, d1)
+        qh.qh_dirs(H, V, d2)
+        assert d1.raw == d2.raw
+
+
 def test_pawn_moves_golden(qh, pawn_cases):
+    qh.qh_pawn_moves_ctx.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+    qh.qh_pawn_moves_ctx.restype = C.c_uint
     for H, V, loc, opp, player, want in pawn_cases:
         got = qh.qh_pawn_moves(H, V, loc, opp, player)
+        assert [a for a in range(12) if got >> a & 1] == want
+        got = qh.qh_pawn_moves_ctx(H, V, loc, opp, player)
         assert [a for a in range(12) if got >> a & 1] == want
 
 
@@ -159,8 +179,11 @@ def test_pawn_moves_vs_oracle_exhaustive_adjacency(qh):
                 if not 0 <= Op <= 80:
                     continue
                 for player in (1, 2):
+                    want = O.valid_pawn_actions(H, V, L, Op, player)
                     got = qh.qh_pawn_moves(H, V, L, Op, player)
-                    assert [a for a in range(12) if got >> a & 1] == O.valid_pawn_actions(H, V, L, Op, player)
+                    assert [a for a in range(12) if got >> a & 1] == want
+                    got = qh.qh_pawn_moves_ctx(H, V, L, Op, player)
+                    assert [a for a in range(12) if got >> a & 1] == want
 
 
 def test_replay_traces(qh, traces):
@@ -278,6 +301,21 @@ def test_philox_and_rollouts_match_oracle(qh):
         g = O.OracleGame().set_position(H, V, p1, p2, w1, w2, cur)
         seed, rid, ply = rng.getrandbits(64), rng.getrandbits(40), rng.randrange(0, 900)
         assert qh.qh_sample_action(s, seed, rid, ply) == g.sample_action(seed, rid, ply)
+    # the table-driven and the capped variants used by the wall-phase kernel agree with the plain sampler
+    qh.qh_sample_action_known.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_uint32]
+    qh.qh_sample_action_capped.argtypes = [C.POINTER(C.c_uint64), C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32]
+    n_capped = 0
+    for it in range(1500):
+        H, V = rand_walls(rng, rng.randrange(12, 21))
+        _, _, p1, p2, w1, w2, cur = _random_position(rng)
+        s = mk_state(qh, H, V, p1, p2, w1, w2, cur)
+        seed, rid, ply = rng.getrandbits(64), rng.getrandbits(40), rng.randrange(0, 900)
+        want = qh.qh_sample_action(s, seed, rid, ply)
+        assert qh.qh_sample_action_known(s, seed, rid, ply) == want
+        capped = qh.qh_sample_action_capped(s, seed, rid, ply, 2)
+        assert capped == want or capped == -2
+        n_capped += capped == -2
+    assert n_capped > 10
     # whole rollouts from the start and from midgames
     for it in range(150):
         if it < 60:
