@@ -82,6 +82,31 @@ def main():
         done = torch.empty(n, dtype=torch.uint8, device="cuda")
         ms = timed(lambda: env.step(acts, done=done))
         out["step"] = {"n": n, "ms": ms, "GBps": n * (24 + 4 + 24 + 1) / ms / 1e6, "steps_per_s": n / ms * 1e3}
+    if "az" in which:
+        from alphazero_quoridor_b200.policy_value_net import PolicyValueNet
+        from alphazero_quoridor_b200 import tree
+        torch.manual_seed(0)
+        net = PolicyValueNet(use_gpu=True)
+        for n, K, npl in ((8192, 1, 24), (8192, 4, 48), (8192, 8, 96)):
+            states = midgame_positions(n, seed=11, min_plies=0, max_plies=40)
+            eng = tree.BatchedMCTS(n, tree.NetEvaluator(net), c_puct=5, n_playout=npl, leaves_per_game=K,
+                                   reuse_tree=False)
+            eng.reset(states)
+            eng.search(8)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            eng.search(npl)
+            b.record()
+            torch.cuda.synchronize()
+            ms = a.elapsed_time(b)
+            out["az_mcts_K%d" % K] = {"games": n, "playouts": npl, "ms": ms, "sims_per_s": n * npl / ms * 1e3}
+        for m in (8192, 65536):
+            st = midgame_positions(m, seed=5)
+            net.evaluate_states(st)
+            ms = timed(lambda: net.evaluate_states(st))
+            out["net_forward_%d" % m] = {"ms": ms, "positions_per_s": m / ms * 1e3,
+                                         "TFLOPs": m * 62.8e6 / ms / 1e9}
     print(json.dumps(out, indent=1))
 
 
