@@ -243,16 +243,8 @@ def run_ours(args):
     playouts = args.games * args.playouts * args.steps
     roll_ms = [a.elapsed_time(b) for a, b, _ in roll_events]
     roll_n = [n for _, _, n in roll_events]
-    stats = torch.tensor([ms, float(env_steps), float(playouts), float(sum(roll_ms)), float(launches)],
-                         dtype=torch.float64, device=dev)
-    if world > 1:
-        mx = stats.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = stats.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms, env_total, playouts_total = mx[0].item(), sm[1].item(), sm[2].item()
-    else:
-        env_total, playouts_total = float(env_steps), float(playouts)
+    from alphazero_quoridor_b200.shard import reduce_stats
+    ms, (env_total, playouts_total) = reduce_stats(ms, [env_steps, playouts], device=dev)   # max time, summed work
 
     # ---- end to end through the C ABI with HOST buffers: states H2D, search, moves/visits/new states D2H ----
     host_states = torch.empty((args.games, 3), dtype=torch.int64).pin_memory()
@@ -285,13 +277,7 @@ def run_ours(args):
     barrier()
     e2e_ms = t0.elapsed_time(t1)
     e2e_env = int(ws[1].item()) + int(m.tree_steps.item()) + args.games * e2e_steps
-    e2e_stats = torch.tensor([e2e_ms, float(e2e_env)], dtype=torch.float64, device=dev)
-    if world > 1:
-        a = e2e_stats.clone()
-        dist.all_reduce(a, op=dist.ReduceOp.MAX)
-        b = e2e_stats.clone()
-        dist.all_reduce(b, op=dist.ReduceOp.SUM)
-        e2e_ms, e2e_env = a[0].item(), b[1].item()
+    e2e_ms, (e2e_env,) = reduce_stats(e2e_ms, [e2e_env], device=dev)
     h2d = args.games * 24
     d2h = args.games * (4 + 140 * 4 + 24)
 

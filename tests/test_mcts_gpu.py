@@ -245,3 +245,25 @@ def test_players_and_self_play_loop(qz):
     h = qz.q.Quoridor()
     mv = pure.choose_action(h)
     assert mv in h.actions()
+
+
+def test_sharding_invariance(qz):
+    """Results are keyed by the GLOBAL game index: 64 games searched as one batch == two shards of 32
+    (what two ranks would own), moves and visit counts identical -- no collective needed."""
+    from alphazero_quoridor_b200.selfplay import BatchedSelfPlay
+    from alphazero_quoridor_b200.shard import shard_range
+
+    def run(lo, hi):
+        sp = BatchedSelfPlay(hi - lo, qz.tree.RolloutEvaluator(seed=5), c_puct=5, n_playout=40, leaves_per_game=4,
+                             pure=True, seed=5, game_id_base=lo)
+        out = []
+        for _ in range(3):
+            mv = sp.step()
+            v, _, _ = sp.mcts.root_stats(temp=1.0)
+            out.append((mv.cpu(), sp.mcts.root_state.cpu().clone()))
+        return out
+    whole = run(0, 64)
+    parts = [run(*shard_range(64, r, 2)) for r in range(2)]
+    for t in range(3):
+        assert torch.equal(whole[t][0], torch.cat([parts[0][t][0], parts[1][t][0]]))
+        assert torch.equal(whole[t][1], torch.cat([parts[0][t][1], parts[1][t][1]]))

@@ -1,0 +1,69 @@
+"""CPU, world_size 2 over gloo: the host-side sharding logic of the multi-GPU path."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from alphazero_quoridor_b200 import shard
+
+
+def test_shard_ranges_partition_the_games():
+    for n in (0, 1, 7, 4096, 65536, 65537):
+        for ws in (1, 2, 3, 4, 8):
+            spans = [shard.shard_range(n, r, ws) for r in range(ws)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+            for g in (0, n // 3, n - 1):
+                if 0 <= g < n:
+                    r = shard.owner_of(g, n, ws)
+                    assert spans[r][0] <= g < spans[r][1]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, ws, port, n_total, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws),
+                      LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        assert shard.world() == (rank, ws, rank)
+        lo, hi = shard.shard_range(n_total, rank, ws)
+        # each rank "computes" a value that depends only on the GLOBAL game index (as the Philox streams do)
+        local = (torch.arange(lo, hi, dtype=torch.int64) * 2654435761 % 1000003).unsqueeze(1)
+        allrows = shard.gather_rows(local, n_total)
+        want = (torch.arange(n_total, dtype=torch.int64) * 2654435761 % 1000003).unsqueeze(1)
+        ok_rows = bool(torch.equal(allrows, want))
+        ms, work = shard.reduce_stats(10.0 + rank, [float(hi - lo), 1.0])
+        q.put((rank, ok_rows, ms, work))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_gloo_reduction_and_gather():
+    ws, n_total = 2, 1001
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, ws, port, n_total, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(ws)]
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, ok_rows, ms, work in res:
+        assert ok_rows
+        assert ms == 11.0                      # max over ranks
+        assert work == [float(n_total), 2.0]   # sum over ranks
