@@ -86,91 +86,172 @@ extern "C" int qz_env_legal_mask(const qz_state *states, uint64_t *mask3, int64_
 }
 
 // ------------------------------------------------------------------------------------------ encode
-// One warp per game.  The warp first builds, per tile, the 26-bit "which planes are hot here" word in
-// shared memory (81 words), then streams the tensor out with fully coalesced 4- or 8-byte stores.
-// HBM-bound by design: 2106 elements written per game, 24 B read.
+// HBM-bound by design: 24 B read and 2106 (NCHW) / 81*c_stride (NHWC) elements written per game.
+// A block of 8 warps encodes 8 games.  Phase 1 builds the block's output as a packed BIT stream in shared
+// memory -- NCHW: 26 plane masks of 81 bits OR-ed in at bit g*2106 + p*81; NHWC with 32 channels: one 32-bit
+// "planes hot on this tile" word per tile.  Phase 2 is then layout-agnostic: output chunk q (8 two-byte or
+// 4 four-byte elements = 16 B) is byte / nibble q of the stream, expanded with integer multiplies and
+// written with one fully coalesced 16-byte store per lane (~1.4 instructions per byte written).
 template <typename T> struct QzOne;
 template <> struct QzOne<float> { static __device__ __forceinline__ uint32_t bits() { return 0x3F800000u; } };
 template <> struct QzOne<__nv_bfloat16> { static __device__ __forceinline__ uint32_t bits() { return 0x3F80u; } };
 template <> struct QzOne<__half> { static __device__ __forceinline__ uint32_t bits() { return 0x3C00u; } };
 
-__device__ __forceinline__ uint32_t qz_tile_word(const QzState &s, int t, int mine, int theirs, uint32_t cbits) {
+#define QZ_ENC_GAMES 8
+#define QZ_ENC_WORDS_NCHW ((QZ_ENC_GAMES * QZ_STATE_ELEMS + 31) / 32 + 1)      // 527 + pad
+#define QZ_ENC_WORDS_NHWC (QZ_ENC_GAMES * 81)
+
+struct QzEncodeView {
+    int mine, theirs;       // tiles of the mover's / opponent's pawn (numpy-wrapped; > 80 lights nothing)
+    uint32_t cbits;         // planes 5..25 that are constant over the board
+};
+
+__device__ __forceinline__ QzEncodeView qz_encode_view(const QzState &s) {
+    const uint64_t m = s.meta;
+    const int cur = qz_cur(m);
+    QzEncodeView v;
+    v.mine = cur == 1 ? qz_p1(m) : qz_p2(m);
+    v.theirs = cur == 1 ? qz_p2(m) : qz_p1(m);
+    if (v.mine < 0) v.mine += 81;                  // numpy negative index wrap (quoridor.py:69,73)
+    if (v.theirs < 0) v.theirs += 81;
+    const int wm = cur == 1 ? qz_w1(m) : qz_w2(m), wo = cur == 1 ? qz_w2(m) : qz_w1(m);
+    const int im = wm - 1 < 0 ? 9 : (wm - 1 > 9 ? 9 : wm - 1);      // index -1 wraps to plane 9 (:79-80)
+    const int io = wo - 1 < 0 ? 9 : (wo - 1 > 9 ? 9 : wo - 1);
+    v.cbits = (1u << (5 + im)) | (1u << (15 + io)) | (cur == 2 ? 1u << 25 : 0u);
+    return v;
+}
+
+// 81-bit mask of plane p (quoridor.py:58-131)
+__device__ __forceinline__ BB qz_plane_mask(const QzState &s, const QzEncodeView &v, int p) {
+    if (p == 0) return bb_spread8(~(s.H | s.V));
+    if (p == 1) return bb_spread8(s.V);
+    if (p == 2) return bb_spread8(s.H);
+    if (p == 3) return (unsigned)v.mine <= 80u ? bb_bit(v.mine) : bb_zero();
+    if (p == 4) return (unsigned)v.theirs <= 80u ? bb_bit(v.theirs) : bb_zero();
+    return ((v.cbits >> p) & 1u) ? bb_make(0xFFFFFFFFu, 0xFFFFFFFFu, QZ_BOARD_W2) : bb_zero();
+}
+
+__device__ __forceinline__ uint32_t qz_tile_word(const QzState &s, int t, const QzEncodeView &v) {
     const int r = t / 9, c = t - 9 * r;
-    uint32_t w = cbits;
+    uint32_t w = v.cbits;
     if (r < 8 && c < 8) {
         const int i = r * 8 + c;
-        const uint32_t h = (uint32_t)(s.H >> i) & 1u, v = (uint32_t)(s.V >> i) & 1u;
-        w |= h ? 4u : (v ? 2u : 1u);
+        const uint32_t h = (uint32_t)(s.H >> i) & 1u, vv = (uint32_t)(s.V >> i) & 1u;
+        w |= h ? 4u : (vv ? 2u : 1u);
     }
-    if (t == mine) w |= 8u;
-    if (t == theirs) w |= 16u;
+    if (t == v.mine) w |= 8u;
+    if (t == v.theirs) w |= 16u;
     return w;
 }
 
+// OR an 81-bit mask into a shared bit stream at bit offset `off`
+__device__ __forceinline__ void qz_or_bits(uint32_t *stream, int off, const BB &b) {
+    const int w = off >> 5, sh = off & 31;
+    const uint64_t lo = (uint64_t)b.w0 << sh, mid = (uint64_t)b.w1 << sh, hi = (uint64_t)b.w2 << sh;
+    const uint32_t x0 = (uint32_t)lo, x1 = (uint32_t)(lo >> 32) | (uint32_t)mid;
+    const uint32_t x2 = (uint32_t)(mid >> 32) | (uint32_t)hi, x3 = (uint32_t)(hi >> 32);
+    if (x0) atomicOr(stream + w, x0);
+    if (x1) atomicOr(stream + w + 1, x1);
+    if (x2) atomicOr(stream + w + 2, x2);
+    if (x3) atomicOr(stream + w + 3, x3);
+}
+
 template <typename T, int LAYOUT>
-__global__ void __launch_bounds__(256) qz_encode_kernel(const qz_state *__restrict__ states, T *__restrict__ out,
-                                                        int c_stride, int64_t n) {
+__global__ void __launch_bounds__(256) qz_encode_kernel(const qz_state *__restrict__ states, T *__restrict__ out, int64_t n) {
+    constexpr int WORDS = LAYOUT == QZ_LAYOUT_NCHW ? QZ_ENC_WORDS_NCHW : QZ_ENC_WORDS_NHWC;
+    constexpr int ELEMS_PER_GAME = LAYOUT == QZ_LAYOUT_NCHW ? QZ_STATE_ELEMS : 81 * 32;
+    constexpr int PER_CHUNK = 16 / (int)sizeof(T);                      // elements per 16-byte store
+    __shared__ __align__(16) uint32_t stream[WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t g0 = (int64_t)blockIdx.x * QZ_ENC_GAMES;
+    const int games = (int)min((int64_t)QZ_ENC_GAMES, n - g0);
+    if (LAYOUT == QZ_LAYOUT_NCHW) {
+        for (int i = threadIdx.x; i < WORDS; i += 256) stream[i] = 0;
+        __syncthreads();
+    }
+    if (warp < games) {
+        const QzState s = qz_load_state(states + g0 + warp);
+        const QzEncodeView v = qz_encode_view(s);
+        if (LAYOUT == QZ_LAYOUT_NCHW) {
+            if (lane < QZ_N_PLANES) qz_or_bits(stream, warp * QZ_STATE_ELEMS + lane * 81, qz_plane_mask(s, v, lane));
+        } else {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int t = lane + 32 * k;
+                if (t < 81) stream[warp * 81 + t] = qz_tile_word(s, t, v);
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t one = QzOne<T>::bits();
+    T *base = out + g0 * (int64_t)ELEMS_PER_GAME;
+    const int total = games * ELEMS_PER_GAME;
+    const int full_chunks = total / PER_CHUNK;
+    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(stream);
+    for (int q = threadIdx.x; q < full_chunks; q += 256) {
+        uint4 o;
+        if (sizeof(T) == 2) {
+            const uint32_t b = bytes[q];
+            o.x = (b & 1u) * one + ((b >> 1) & 1u) * (one << 16);
+            o.y = ((b >> 2) & 1u) * one + ((b >> 3) & 1u) * (one << 16);
+            o.z = ((b >> 4) & 1u) * one + ((b >> 5) & 1u) * (one << 16);
+            o.w = ((b >> 6) & 1u) * one + ((b >> 7) & 1u) * (one << 16);
+        } else {
+            const uint32_t b = (bytes[q >> 1] >> ((q & 1) * 4)) & 0xFu;
+            o.x = (b & 1u) * one; o.y = ((b >> 1) & 1u) * one; o.z = ((b >> 2) & 1u) * one; o.w = ((b >> 3) & 1u) * one;
+        }
+        *reinterpret_cast<uint4 *>(base + (int64_t)q * PER_CHUNK) = o;
+    }
+    // tail of a partial last block (total not a multiple of the chunk size)
+    for (int e = full_chunks * PER_CHUNK + threadIdx.x; e < total; e += 256) {
+        const uint32_t bit = (stream[e >> 5] >> (e & 31)) & 1u;
+        if (sizeof(T) == 2) reinterpret_cast<uint16_t *>(base)[e] = (uint16_t)(bit * one);
+        else reinterpret_cast<uint32_t *>(base)[e] = bit * one;
+    }
+}
+
+// generic channel stride for NHWC (c_stride != 32): one warp per game, 4-byte stores
+template <typename T>
+__global__ void __launch_bounds__(256) qz_encode_nhwc_generic_kernel(const qz_state *__restrict__ states, T *__restrict__ out,
+                                                                     int c_stride, int64_t n) {
     __shared__ uint32_t words[8][84];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t g = (int64_t)blockIdx.x * 8 + warp;
     if (g >= n) return;
     const QzState s = qz_load_state(states + g);
-    const uint64_t m = s.meta;
-    const int cur = qz_cur(m);
-    int mine = cur == 1 ? qz_p1(m) : qz_p2(m), theirs = cur == 1 ? qz_p2(m) : qz_p1(m);
-    if (mine < 0) mine += 81;                 // numpy negative index wrap (quoridor.py:69,73)
-    if (theirs < 0) theirs += 81;
-    const int wm = cur == 1 ? qz_w1(m) : qz_w2(m), wo = cur == 1 ? qz_w2(m) : qz_w1(m);
-    const int im = wm - 1 < 0 ? 9 : (wm - 1 > 9 ? 9 : wm - 1);      // index -1 wraps to plane 9 (:79-80)
-    const int io = wo - 1 < 0 ? 9 : (wo - 1 > 9 ? 9 : wo - 1);
-    const uint32_t cbits = (1u << (5 + im)) | (1u << (15 + io)) | (cur == 2 ? 1u << 25 : 0u);
+    const QzEncodeView v = qz_encode_view(s);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         const int t = lane + 32 * k;
-        if (t < 81) words[warp][t] = qz_tile_word(s, t, mine, theirs, cbits);
+        if (t < 81) words[warp][t] = qz_tile_word(s, t, v);
     }
     __syncwarp();
     const uint32_t one = QzOne<T>::bits();
-    if (LAYOUT == QZ_LAYOUT_NCHW) {
-        T *base = out + g * (int64_t)QZ_STATE_ELEMS;
-        // element pairs (e, e+1), e even; 2106 is even so pairs never straddle games
-        for (int q = lane; q < QZ_STATE_ELEMS / 2; q += 32) {
-            const int e0 = 2 * q, e1 = e0 + 1;
-            const int p0 = e0 / 81, t0 = e0 - 81 * p0;
-            const int p1 = e1 / 81, t1 = e1 - 81 * p1;
-            const uint32_t b0 = (words[warp][t0] >> p0) & 1u, b1 = (words[warp][t1] >> p1) & 1u;
-            if (sizeof(T) == 4) {
-                uint2 v; v.x = b0 ? one : 0u; v.y = b1 ? one : 0u;
-                *reinterpret_cast<uint2 *>(base + e0) = v;
-            } else {
-                *reinterpret_cast<uint32_t *>(base + e0) = (b0 ? one : 0u) | ((b1 ? one : 0u) << 16);
-            }
-        }
-    } else {
-        T *base = out + g * (int64_t)81 * c_stride;      // c_stride is even (checked by the host)
-        const int total = 81 * c_stride / 2;
-        for (int q = lane; q < total; q += 32) {
-            const int e0 = 2 * q;
-            const int t = e0 / c_stride, c0 = e0 - t * c_stride;
-            const uint32_t wv = words[warp][t];
-            const uint32_t b0 = c0 < 26 ? (wv >> c0) & 1u : 0u, b1 = c0 + 1 < 26 ? (wv >> (c0 + 1)) & 1u : 0u;
-            if (sizeof(T) == 4) {
-                uint2 v; v.x = b0 ? one : 0u; v.y = b1 ? one : 0u;
-                *reinterpret_cast<uint2 *>(base + e0) = v;
-            } else {
-                *reinterpret_cast<uint32_t *>(base + e0) = (b0 ? one : 0u) | ((b1 ? one : 0u) << 16);
-            }
+    T *base = out + g * (int64_t)81 * c_stride;          // c_stride is even (checked by the host)
+    const int total = 81 * c_stride / 2;
+    for (int q = lane; q < total; q += 32) {
+        const int e0 = 2 * q;
+        const int t = e0 / c_stride, c0 = e0 - t * c_stride;
+        const uint32_t wv = words[warp][t];
+        const uint32_t b0 = c0 < 26 ? (wv >> c0) & 1u : 0u, b1 = c0 + 1 < 26 ? (wv >> (c0 + 1)) & 1u : 0u;
+        if (sizeof(T) == 4) {
+            uint2 o; o.x = b0 * one; o.y = b1 * one;
+            *reinterpret_cast<uint2 *>(base + e0) = o;
+        } else {
+            *reinterpret_cast<uint32_t *>(base + e0) = b0 * one | (b1 * one) << 16;
         }
     }
 }
 
 template <typename T>
 static int qz_encode_launch(const qz_state *states, void *out, int layout, int c_stride, int64_t n, cudaStream_t st) {
-    const unsigned blocks = qz_blocks_for(n, 8);
+    const unsigned blocks = qz_blocks_for(n, QZ_ENC_GAMES);
     if (layout == QZ_LAYOUT_NCHW)
-        qz_encode_kernel<T, QZ_LAYOUT_NCHW><<<blocks, 256, 0, st>>>(states, (T *)out, 26, n);
+        qz_encode_kernel<T, QZ_LAYOUT_NCHW><<<blocks, 256, 0, st>>>(states, (T *)out, n);
+    else if (c_stride == 32)
+        qz_encode_kernel<T, QZ_LAYOUT_NHWC><<<blocks, 256, 0, st>>>(states, (T *)out, n);
     else
-        qz_encode_kernel<T, QZ_LAYOUT_NHWC><<<blocks, 256, 0, st>>>(states, (T *)out, c_stride, n);
+        qz_encode_nhwc_generic_kernel<T><<<blocks, 256, 0, st>>>(states, (T *)out, c_stride, n);
     return qz_check_launch("qz_env_encode");
 }
 
@@ -184,7 +265,7 @@ extern "C" int qz_env_encode(const qz_state *states, void *out, int dtype, int l
     QZ_REQUIRE_PTR(states);
     QZ_REQUIRE_PTR(out);
     QZ_REQUIRE_ALIGN(states, 8);
-    QZ_REQUIRE_ALIGN(out, 8);
+    QZ_REQUIRE_ALIGN(out, 16);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == QZ_DTYPE_F32) return qz_encode_launch<float>(states, out, layout, c_stride, n, st);
     if (dtype == QZ_DTYPE_BF16) return qz_encode_launch<__nv_bfloat16>(states, out, layout, c_stride, n, st);

@@ -135,17 +135,27 @@ def test_rollout_is_launch_shape_invariant(qz):
 
 def test_encode_dtypes_and_layouts(qz):
     from alphazero_quoridor_b200.synthetic import midgame_positions
-    states = midgame_positions(1000, seed=5)
-    env = qz.BatchedQuoridor(states.shape[0], states=states)
+    states = midgame_positions(1003, seed=5)[:1003]          # not a multiple of the 8 games per block
+    n = states.shape[0]
+    env = qz.BatchedQuoridor(n, states=states)
     ref = env.encode(dtype=torch.float32)
-    assert ref.shape == (1000, 26, 9, 9)
-    assert torch.equal(ref.sum(dim=(2, 3))[:, 3:5], torch.ones(1000, 2, device=ref.device))
+    assert ref.shape == (n, 26, 9, 9)
+    assert torch.equal(ref.sum(dim=(2, 3))[:, 3:5], torch.ones(n, 2, device=ref.device))
+    # against the rules header's plane definition evaluated on the host oracle for a few games
+    for i in (0, 1, 7, 8, n - 1):
+        d = env.host_states()[i]
+        g = O.OracleGame().set_position(d["H"], d["V"], d["p1"], d["p2"], d["w1"], d["w2"], d["cur"])
+        assert np.array_equal(ref[i].cpu().numpy().astype(np.float64), g.state())
+    for m in (1, 3, 9):                                      # tiny batches: partial blocks only
+        sub = qz.BatchedQuoridor(m, states=states[:m].clone())
+        assert torch.equal(sub.encode(dtype=torch.bfloat16).float(), ref[:m])
+        assert torch.equal(sub.encode(dtype=torch.float32), ref[:m])
     for dt in (torch.bfloat16, torch.float16):
         assert torch.equal(env.encode(dtype=dt).float(), ref)
     for dt in (torch.float32, torch.bfloat16):
         for cs in (26, 32):
             cl = env.encode(dtype=dt, channels_last=True, c_stride=cs)
-            assert cl.shape == (1000, cs, 9, 9) and cl.is_contiguous(memory_format=torch.channels_last)
+            assert cl.shape == (n, cs, 9, 9) and cl.is_contiguous(memory_format=torch.channels_last)
             assert torch.equal(cl[:, :26].float(), ref)
             assert cl[:, 26:].abs().sum().item() == 0
 
