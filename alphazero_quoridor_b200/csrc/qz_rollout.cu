@@ -26,8 +26,10 @@ struct QzRolloutArgs {
     int8_t *result;                // [n_rollouts] +1/-1/0 from the starting mover's view
     int32_t *plies;                // nullable [n_rollouts]
     qz_state *final_states;        // nullable [n_rollouts]
-    unsigned long long *counter;   // [0] phase-1 work counter, [1] cumulative plies, [2] phase-2 work counter
-    qz_state *mid;                 // [n_rollouts] state at the end of the wall phase
+    unsigned long long *counter;   // [0] wall-phase work counter, [1] cumulative plies, [2] pawn-phase work counter,
+                                   // [3] number of ejected ("stuck") rollouts, [4] stuck-phase work counter
+    qz_state *mid;                 // [n_rollouts] state when a rollout leaves a phase
+    int32_t *stuck_list;           // [n_rollouts] rollouts ejected from the wall phase
 };
 
 // Warp-aggregated claim of the next unstarted rollout for every idle lane; returns -1 when none is left.
@@ -55,30 +57,19 @@ __device__ __forceinline__ int64_t qz_start_index(const QzRolloutArgs &a, int64_
 // state is parked in `mid` for phase 2.
 //
 // A rollout whose mover keeps drawing walls that fail the path check ("stuck": walls in hand, next to no
-// legal placement -- under 1% of rollouts but 60% of all path checks when every draw costs two flood fills)
-// is switched to warp-cooperative plies: its state is broadcast, the whole warp computes the exact legal set
-// with one 128-candidate sweep (qz_warp_legal), and the owner lane replays the SAME draw sequence against
-// that table.  Same action as the per-lane path, bit for bit.
+// legal placement) is under 1 % of the rollouts but cost 60 % of all path checks and, worse, a serial tail:
+// hundreds of plies of up to 40 rejected draws each on ONE lane (profiles/r1b_rollout_wall_ncu_full.txt: SMs
+// active 15 % of the kernel's duration).  Such a rollout is therefore EJECTED from this kernel after
+// QZ_MAX_REJECTS failed draws in one ply and finished by qz_rollout_stuck_kernel, where a whole block sweeps
+// all candidates of a ply in parallel.
 #define QZ_MAX_REJECTS 2u
-#define QZ_MAX_SWEEPS_PER_ITER 6      // more stuck lanes than this in one warp: cheaper to let every lane grind on
-
-// out of line: keeps the second copy of the flood-fill code (and its registers) out of the per-lane hot loop
-__device__ __noinline__ void qz_warp_legal_call(uint64_t H, uint64_t V, uint64_t meta, uint32_t *pawn, uint64_t *hl,
-                                                uint64_t *vl) {
-    QzState t;
-    t.H = H; t.V = V; t.meta = meta;
-    uint32_t p; uint64_t a, b;
-    qz_warp_legal(t, p, a, b);
-    *pawn = p; *hl = a; *vl = b;
-}
 
 __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a) {
-    const int lane = threadIdx.x & 31;
     QzState s;
     QzRng rng;
     int64_t r = -1;
     int steps = 0;
-    bool exhausted = false, stuck = false;
+    bool exhausted = false;
     s.H = s.V = s.meta = 0;
     rng = qz_rng_init(0, 0);
     for (;;) {
@@ -90,49 +81,92 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
                 s = qz_load_state(a.states + qz_start_index(a, r));
                 rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + r) : a.rid_base + (uint64_t)r);
                 steps = 0;
-                stuck = false;
             } else {
                 exhausted = true;
             }
         }
         if (__all_sync(QZ_FULL_MASK, r < 0)) break;
-        bool leave = false, need_sweep = false;
-        if (r >= 0) leave = qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0;
-        const bool live = r >= 0 && !leave;
-        // lanes already known to be stuck go straight to the warp sweep -- unless the warp is full of them
-        const bool pre = live && stuck && qz_mover_walls(s.meta) > 0;
-        const unsigned pre_mask = __ballot_sync(QZ_FULL_MASK, pre);
-        const bool crowded = __popc(pre_mask) > QZ_MAX_SWEEPS_PER_ITER;
-        if (live) {
-            if (pre && !crowded) {
-                need_sweep = true;
-            } else {
-                const int act = qz_sample_action_capped(s, rng, (uint32_t)steps, crowded ? 0xFFFFFFFFu : QZ_MAX_REJECTS);
-                if (act == -2) { stuck = true; need_sweep = true; }
-                else if (act < 0) { s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40; leave = true; }
-                else { s = qz_apply(s, act); steps++; }
+        if (r >= 0) {
+            bool leave = qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0;
+            if (!leave) {
+                const int act = qz_sample_action_capped(s, rng, (uint32_t)steps, QZ_MAX_REJECTS);
+                if (act == -2) {                                        // stuck: hand over to the block-per-rollout kernel
+                    const unsigned long long k = atomicAdd(a.counter + 3, 1ull);
+                    a.stuck_list[k] = (int32_t)r;
+                    leave = true;
+                } else if (act < 0) {
+                    s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40;
+                    leave = true;
+                } else {
+                    s = qz_apply(s, act);
+                    steps++;
+                }
+            }
+            if (leave) {
+                qz_store_state(a.mid + r, s);
+                r = -1;
             }
         }
-        unsigned sweep_mask = __ballot_sync(QZ_FULL_MASK, need_sweep);
-        while (sweep_mask) {
-            const int l = __ffs(sweep_mask) - 1;
-            sweep_mask &= sweep_mask - 1;
-            QzState t;
-            t.H = __shfl_sync(QZ_FULL_MASK, s.H, l);
-            t.V = __shfl_sync(QZ_FULL_MASK, s.V, l);
-            t.meta = __shfl_sync(QZ_FULL_MASK, s.meta, l);
-            uint32_t pawn; uint64_t hl, vl;
-            qz_warp_legal_call(t.H, t.V, t.meta, &pawn, &hl, &vl);
-            if (lane == l) {
-                const int act = qz_sample_action_known(s, rng, (uint32_t)steps, pawn, hl, vl);
-                if (act < 0) { s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40; leave = true; }
-                else { s = qz_apply(s, act); steps++; }
+    }
+}
+
+// ---- phase 1b: stuck rollouts, one block per rollout ---------------------------------------------------------
+// Every thread tracks the same state redundantly (no broadcasts).  On a ply whose mover owns walls the block
+// runs the full sweep with one flood fill per thread (task = candidate x player), gathers the failures in
+// shared memory, and every thread replays the specified draw sequence against the resulting table
+// (qz_sample_action_known) -- the same action the per-lane path would take, at a latency of ~one flood fill
+// per ply instead of up to 80.
+#define QZ_STUCK_THREADS 128
+
+__global__ void __launch_bounds__(QZ_STUCK_THREADS, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
+    __shared__ unsigned long long fail_h, fail_v;
+    __shared__ long long sh_entry;
+    const int tid = threadIdx.x;
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned long long k = atomicAdd(a.counter + 4, 1ull);
+            sh_entry = k < a.counter[3] ? (long long)a.stuck_list[k] : -1;
+        }
+        __syncthreads();
+        const int64_t r = sh_entry;
+        if (r < 0) break;
+        QzState s = qz_load_state(a.mid + r);
+        const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, r)) + 2);
+        int steps = (int)qz_ply(s.meta) - (int)qz_ply(m0);
+        QzRng rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + r) : a.rid_base + (uint64_t)r);
+        for (;;) {
+            if (qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0) break;
+            const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+            const uint32_t pawn = qz_mover_pawn_moves_ctx(c, s.meta);
+            uint64_t hl = 0, vl = 0;
+            if (qz_mover_walls(s.meta) > 0) {
+                const uint64_t hc = qz_hcand(s.H, s.V), vc = qz_vcand(s.H, s.V);
+                const int nh = qz_popc64(hc), total = nh + qz_popc64(vc);
+                if (tid == 0) { fail_h = 0; fail_v = 0; }
+                __syncthreads();
+                const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
+                for (int task = tid; task < 2 * total; task += QZ_STUCK_THREADS) {
+                    const int k = task >> 1, player = (task & 1) + 1;
+                    const bool vert = k >= nh;
+                    const int ix = qz_nth_bit64(vert ? vc : hc, vert ? k - nh : k);
+                    QzDirs d = w.dirs;
+                    uint64_t H = s.H, V = s.V;
+                    if (vert) { qz_dirs_place_v(d, ix); V |= 1ull << ix; } else { qz_dirs_place_h(d, ix); H |= 1ull << ix; }
+                    const bool ok = player == 1 ? qz_reaches_goal(d, w.p1, w.p2, 1, H, V) : qz_reaches_goal(d, w.p2, w.p1, 2, H, V);
+                    if (!ok) atomicOr(vert ? &fail_v : &fail_h, 1ull << ix);
+                }
+                __syncthreads();
+                hl = hc & ~fail_h;
+                vl = vc & ~fail_v;
+                __syncthreads();                    // everyone has read the table before the next ply clears it
             }
+            const int act = qz_sample_action_known(s, rng, (uint32_t)steps, pawn, hl, vl);
+            if (act < 0) { s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40; break; }
+            s = qz_apply(s, act);
+            steps++;
         }
-        if (r >= 0 && leave) {
-            qz_store_state(a.mid + r, s);
-            r = -1;
-        }
+        if (tid == 0) qz_store_state(a.mid + r, s);
     }
 }
 
@@ -205,17 +239,18 @@ __global__ void __launch_bounds__(128) qz_rollout_pawn_kernel(QzRolloutArgs a) {
 }
 
 extern "C" int64_t qz_rollout_workspace_bytes(int64_t n_rollouts) {
-    return 32 + (n_rollouts > 0 ? n_rollouts : 0) * (int64_t)sizeof(qz_state);
+    const int64_t n = n_rollouts > 0 ? n_rollouts : 0;
+    return 64 + n * (int64_t)sizeof(qz_state) + ((n * 4 + 7) / 8) * 8;
 }
 
-static int qz_persistent_blocks(const void *kernel, int64_t n_rollouts) {
+static int qz_persistent_blocks(const void *kernel, int64_t n_items, int items_per_block) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
     int64_t blocks = (int64_t)sms * per_sm;                 // one resident wave: a multiple of the SM count
-    const int64_t needed = (n_rollouts + 127) / 128;
+    const int64_t needed = (n_items + items_per_block - 1) / items_per_block;
     return (int)(blocks < needed ? blocks : needed);
 }
 
@@ -234,17 +269,22 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
     cudaStream_t st = (cudaStream_t)stream;
     unsigned long long *ctr = (unsigned long long *)workspace;
     cudaError_t e = cudaMemsetAsync(ctr, 0, 8, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctr + 2, 0, 8, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctr + 2, 0, 24, st);
     if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout: memset: %s", cudaGetErrorString(e));
     QzRolloutArgs a;
     a.states = states; a.state_index = state_index; a.rids = rids; a.rid_base = rid_base; a.seed = seed;
     a.n_rollouts = n_rollouts; a.per_state = per_state > 0 ? per_state : 1; a.limit = limit;
     a.result = result; a.plies = plies; a.final_states = final_states;
     a.counter = ctr;
-    a.mid = (qz_state *)((char *)workspace + 32);
-    qz_rollout_wall_kernel<<<qz_persistent_blocks((const void *)qz_rollout_wall_kernel, n_rollouts), 128, 0, st>>>(a);
+    a.mid = (qz_state *)((char *)workspace + 64);
+    a.stuck_list = (int32_t *)((char *)workspace + 64 + n_rollouts * (int64_t)sizeof(qz_state));
+    qz_rollout_wall_kernel<<<qz_persistent_blocks((const void *)qz_rollout_wall_kernel, n_rollouts, 128), 128, 0, st>>>(a);
     int rc = qz_check_launch("qz_rollout (wall phase)");
     if (rc) return rc;
-    qz_rollout_pawn_kernel<<<qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts), 128, 0, st>>>(a);
+    // the number of ejected rollouts is only known on the device: launch a resident grid, blocks exit when the list is empty
+    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1), QZ_STUCK_THREADS, 0, st>>>(a);
+    rc = qz_check_launch("qz_rollout (stuck phase)");
+    if (rc) return rc;
+    qz_rollout_pawn_kernel<<<qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, 128), 128, 0, st>>>(a);
     return qz_check_launch("qz_rollout (pawn phase)");
 }

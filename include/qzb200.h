@@ -119,11 +119,11 @@ int qz_env_encode(const qz_state *states, void *out, int dtype, int layout, int 
  *   limit                the reference's `limit` (1000): at most limit-1 plies are played.
  *   result[r]            +1 / -1 from the STARTING mover's point of view, 0 if nobody won (:104-108).
  *   plies[r]             (nullable) plies played.     final_states[r]  (nullable) where the rollout ended.
- *   workspace            qz_rollout_workspace_bytes(n_rollouts) bytes of device scratch (8-byte aligned): 64-bit
- *                        words 0 and 2 are the two phases' work counters (zeroed by the call); word 1 ACCUMULATES
- *                        the plies played by every call (caller zeroes / reads it), i.e. the env-step count without
- *                        a per-rollout reduction; from byte 32 on, one qz_state per rollout parks the position
- *                        between the wall phase and the pawn phase (two kernels).
+ *   workspace            qz_rollout_workspace_bytes(n_rollouts) bytes of device scratch (8-byte aligned).  64-bit
+ *                        words 0, 2, 3, 4 are work / list counters (zeroed by the call); word 1 ACCUMULATES the
+ *                        plies played by every call (caller zeroes / reads it), i.e. the env-step count without a
+ *                        per-rollout reduction; from byte 64 on, one qz_state per rollout parks the position between
+ *                        the phases (wall, stuck, pawn: three kernels), followed by the list of ejected rollouts.
  */
 int64_t qz_rollout_workspace_bytes(int64_t n_rollouts);
 int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
