@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
 __global__ void __launch_bounds__(QZ_STUCK_THREADS, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
     __shared__ unsigned long long fail_h, fail_v;
     __shared__ long long sh_entry;
+    __shared__ int sh_first[QZ_STUCK_THREADS / 32];
     const int tid = threadIdx.x;
     for (;;) {
         __syncthreads();
@@ -139,9 +140,9 @@ __global__ void __launch_bounds__(QZ_STUCK_THREADS, 4) qz_rollout_stuck_kernel(Q
             if (qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0) break;
             const QzPawnCtx c = qz_ctx_build(s.H, s.V);
             const uint32_t pawn = qz_mover_pawn_moves_ctx(c, s.meta);
-            uint64_t hl = 0, vl = 0;
+            uint64_t hl = 0, vl = 0, hc = 0, vc = 0;
             if (qz_mover_walls(s.meta) > 0) {
-                const uint64_t hc = qz_hcand(s.H, s.V), vc = qz_vcand(s.H, s.V);
+                hc = qz_hcand(s.H, s.V); vc = qz_vcand(s.H, s.V);
                 const int nh = qz_popc64(hc), total = nh + qz_popc64(vc);
                 if (tid == 0) { fail_h = 0; fail_v = 0; }
                 __syncthreads();
@@ -161,7 +162,25 @@ __global__ void __launch_bounds__(QZ_STUCK_THREADS, 4) qz_rollout_stuck_kernel(Q
                 vl = vc & ~fail_v;
                 __syncthreads();                    // everyone has read the table before the next ply clears it
             }
-            const int act = qz_sample_action_known(s, rng, (uint32_t)steps, pawn, hl, vl);
+            // the attempts of qz_sample.cuh are independent draws: thread i evaluates attempt round*128 + i against
+            // the table and the first legal one wins -- the action qz_sample_action_known would return
+            const int npawn = qz_popc32(pawn), nh2 = qz_popc64(hc);
+            const uint32_t M = (uint32_t)(npawn + nh2 + qz_popc64(vc));
+            int act = -1;
+            if (M != 0 && !(npawn == 0 && (hl | vl) == 0)) {
+                for (uint32_t round = 0; act < 0; round++) {
+                    const uint32_t word = qz_attempt_word(rng, (uint32_t)steps, round * QZ_STUCK_THREADS + tid);
+                    const int cand = qz_superset_action(pawn, hc, vc, npawn, nh2, (int)qz_mulhi32(word, M));
+                    const bool legal = cand < 12 || (cand < 76 ? (hl >> (cand - 12)) & 1ull : (vl >> (cand - 76)) & 1ull);
+                    const unsigned bal = __ballot_sync(QZ_FULL_MASK, legal);
+                    const int first = bal ? __shfl_sync(QZ_FULL_MASK, cand, __ffs(bal) - 1) : -1;
+                    if ((tid & 31) == 0) sh_first[tid >> 5] = first;
+                    __syncthreads();
+#pragma unroll
+                    for (int wq = QZ_STUCK_THREADS / 32 - 1; wq >= 0; wq--) if (sh_first[wq] >= 0) act = sh_first[wq];
+                    __syncthreads();
+                }
+            }
             if (act < 0) { s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40; break; }
             s = qz_apply(s, act);
             steps++;

@@ -127,19 +127,12 @@ def cpu_pure_mcts_sample(args, target_s, threads=0):
     steps, playouts, _ = O.pure_mcts_moves(np.repeat(H, g), np.repeat(V, g), np.repeat(meta, g, 0), p,
                                            c_puct=args.c_puct, seed=args.seed + 1, threads=cores, literal_rollouts=True)
     dt = time.perf_counter() - t0
-    # for context: the same port with the product's sampled-legality rollout (one path check per wall ply)
-    t1 = time.perf_counter()
-    s2, _, _ = O.pure_mcts_moves(np.repeat(H, g), np.repeat(V, g), np.repeat(meta, g, 0), p,
-                                 c_puct=args.c_puct, seed=args.seed + 1, threads=cores, literal_rollouts=False)
-    dt2 = time.perf_counter() - t1
     info = {"value": steps / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": "%d start-position games x %d playouts (fresh tree each), %.1f s on %d host threads; "
                       "oracle/quoridor_oracle.c: literal quoridor.py rules + pure_mcts.py:66-115, one full actions() "
                       "sweep per rollout ply (the reference's 2 further recomputations per ply, quoridor.py:165 and "
                       "pure_mcts.py:9-10, are not repeated)" % (g, p, dt, cores),
-            "playouts_per_s": playouts / dt, "seconds": dt,
-            "port_with_sampled_legality": {"value": s2 / dt2, "unit": UNIT,
-                                           "note": "same port, rollout plies verify only the drawn wall (the product's algorithm)"}}
+            "playouts_per_s": playouts / dt, "seconds": dt}
     return info
 
 

@@ -528,50 +528,36 @@ static int nth_set_bit64(uint64_t m, int k) {
 }
 
 /*
- * One uniformly random legal action (pure_mcts.py:7-10 + :99: argmax of iid U(0,1) over the legal
- * list == a uniform pick).  The draw is made from the cheap superset {legal pawn moves} U {walls
- * passing the prechecks of quoridor.py:432-461} and a wall is accepted iff the reference's
- * _validate_* accepts it; rejected candidates are removed and the draw repeated.  Conditional
- * on acceptance the pick is uniform over actions(), and the procedure is specified exactly
- * (DESIGN.md "rollout sampling") so the device kernel reproduces it bit for bit:
- *   attempt 0 of ply t uses word (t & 3) of Philox(ctr = (rid_lo, rid_hi, t >> 2, 0));
- *   attempt j >= 1   uses word 0       of Philox(ctr = (rid_lo, rid_hi, t, j));
- *   index = (word * M) >> 32 over M = |pawn| + |Hc| + |Vc| remaining candidates, taken in the order
- *   pawn ids ascending, then H candidates by ix, then V candidates by ix.
+ * One uniformly random legal action (pure_mcts.py:7-10 + :99: argmax of iid U(0,1) over the legal list == a
+ * uniform pick), by the draw procedure the product specifies (csrc/qz_sample.cuh) restated on top of the
+ * LITERAL rules: the legal list is actions() (every wall verified by the reference's BFS); the ordered superset
+ * S is the legal pawn moves followed by the walls passing the prechecks of quoridor.py:432-461 (H by ix, then V);
+ *   attempt 0 of ply t uses word (t & 3)       of Philox(ctr = (rid_lo, rid_hi, t >> 2, 0));
+ *   attempt j >= 1     uses word ((j - 1) & 3) of Philox(ctr = (rid_lo, rid_hi, t, 1 + ((j - 1) >> 2)));
+ *   the attempt draws S[(word * M) >> 32] (with replacement) and stops if that action is in actions().
  * Returns the action, or -1 when nothing is legal (stalemate).
  */
 int oq_sample_action(const oq_game *g, uint64_t seed, uint64_t rid, uint32_t ply) {
     int player = g->current_player, opp = player == 1 ? 2 : 1;
+    int legal[140], is_legal[140];
+    int nl = oq_actions(g, legal);
+    memset(is_legal, 0, sizeof(is_legal));
+    for (int i = 0; i < nl; i++) is_legal[legal[i]] = 1;
+    int S[140], M = 0;
     int pawn[12];
     int np_ = oq_valid_pawn_actions(g->intersections, g->positions[player], g->positions[opp], player, pawn);
-    uint32_t pmask = 0;
-    for (int i = 0; i < np_; i++) pmask |= 1u << pawn[i];
-    uint64_t hc = 0, vc = 0;
+    for (int i = 0; i < np_; i++) S[M++] = pawn[i];
     if (g->walls_remaining[player] > 0) {
-        for (int ix = 0; ix < 64; ix++) {
-            if (oq_precheck(g, ix, OQ_H)) hc |= 1ull << ix;
-            if (oq_precheck(g, ix, OQ_V)) vc |= 1ull << ix;
-        }
+        for (int ix = 0; ix < 64; ix++) if (oq_precheck(g, ix, OQ_H)) S[M++] = 12 + ix;
+        for (int ix = 0; ix < 64; ix++) if (oq_precheck(g, ix, OQ_V)) S[M++] = 76 + ix;
     }
+    if (M == 0 || nl == 0) return -1;
     for (uint32_t j = 0;; j++) {
-        int npawn = __builtin_popcount(pmask), nh = __builtin_popcountll(hc), nv = __builtin_popcountll(vc);
-        uint32_t M = (uint32_t)(npawn + nh + nv);
-        if (M == 0) return -1;
         uint32_t w[4], word;
         if (j == 0) { oq_philox(seed, rid, ply >> 2, 0, w); word = w[ply & 3]; }
-        else { oq_philox(seed, rid, ply, j, w); word = w[0]; }
-        int k = (int)(((uint64_t)word * M) >> 32);
-        if (k < npawn) return nth_set_bit64(pmask, k);
-        k -= npawn;
-        if (k < nh) {
-            int ix = nth_set_bit64(hc, k);
-            if (!oq_blocks_path(g, ix, OQ_H)) return 12 + ix;
-            hc &= ~(1ull << ix);
-        } else {
-            int ix = nth_set_bit64(vc, k - nh);
-            if (!oq_blocks_path(g, ix, OQ_V)) return 76 + ix;
-            vc &= ~(1ull << ix);
-        }
+        else { oq_philox(seed, rid, ply, 1u + ((j - 1u) >> 2), w); word = w[(j - 1u) & 3u]; }
+        int a = S[(int)(((uint64_t)word * (uint32_t)M) >> 32)];
+        if (is_legal[a]) return a;
     }
 }
 

@@ -24,7 +24,9 @@ SO = os.path.join(HERE, "host_harness", "_build", "libqzhost.so")
 @pytest.fixture(scope="module")
 def qh():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
-    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(SRC), os.path.getmtime(HDR)):
+    csrc = os.path.dirname(HDR)
+    deps = [SRC] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+    if not os.path.exists(SO) or os.path.getmtime(SO) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-o", SO, SRC])
     L = C.CDLL(SO)
