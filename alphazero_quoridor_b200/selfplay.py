@@ -52,9 +52,27 @@ class BatchedSelfPlay:
         gid = self._slot + self.games_started * (1 << 20)
         self.mcts.game_id.copy_(gid * self.stride if isinstance(self.mcts.evaluator, RolloutEvaluator) else gid)
 
-    def step(self):
+    def wave_plan(self):
+        """Leaves per wave of one move's search (mirrors BatchedMCTS.search)."""
         m = self.mcts
-        m.search()
+        plan, done, first = [], 0, True
+        while done < m.n_playout:
+            k = 1 if first else min(m.K, m.n_playout - done)
+            plan.append(k)
+            done += k
+            first = False
+        return plan
+
+    def finish_move(self):
+        """Everything of step() after the search."""
+        return self._after_search()
+
+    def step(self):
+        self.mcts.search()
+        return self._after_search()
+
+    def _after_search(self):
+        m = self.mcts
         if self.pure:
             moves = m.choose(mode=0)
         else:
@@ -78,7 +96,7 @@ class BatchedSelfPlay:
         ply = (meta >> 48) & 0xFFFF
         trunc = (~done) & (ply >= self.max_plies)
         over = done | trunc
-        if not bool(over.any()):
+        if self.record and not bool(over.any()):      # recording flushes on the host; otherwise stay asynchronous
             return
         winner = (meta >> 41) & 3
         self.finished_games += over.sum()
@@ -107,3 +125,45 @@ class BatchedSelfPlay:
             if w:
                 z = torch.where(mover == w, torch.ones_like(z), -torch.ones_like(z))
             self.sink.append((st, pr, z))
+
+
+class StreamedSelfPlay:
+    """S independent `BatchedSelfPlay` sub-batches, each on its own CUDA stream, with their MCTS waves issued
+    round-robin.  Rollout lengths are heavy-tailed (a wave ends with a few very long rollouts running on a few
+    SMs), so interleaving sub-batches lets one sub-batch's tail overlap another's bulk work.  Games keep their
+    global indices (`game_id_base + i`), so results are identical to the un-streamed engine."""
+
+    def __init__(self, n_games, make_evaluator, n_streams=4, game_id_base=0, device=None, **kw):
+        assert n_games % n_streams == 0
+        per = n_games // n_streams
+        self.device = torch.device(device if device is not None else "cuda")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)]
+        self.subs = []
+        for i, st in enumerate(self.streams):
+            with torch.cuda.stream(st):
+                self.subs.append(BatchedSelfPlay(per, make_evaluator(), game_id_base=game_id_base + i * per,
+                                                 device=self.device, **kw))
+        self.n = n_games
+        torch.cuda.synchronize(self.device)
+
+    @property
+    def moves_played(self):
+        return sum(s.moves_played for s in self.subs)
+
+    def step(self):
+        cur = torch.cuda.current_stream(self.device)
+        for st in self.streams:
+            st.wait_stream(cur)
+        plans = [s.wave_plan() for s in self.subs]
+        for w in range(max(len(p) for p in plans)):
+            for sub, st, plan in zip(self.subs, self.streams, plans):
+                if w < len(plan):
+                    with torch.cuda.stream(st):
+                        sub.mcts.playout_wave(plan[w])
+        for sub, st in zip(self.subs, self.streams):
+            with torch.cuda.stream(st):
+                sub.finish_move()
+        for st in self.streams:
+            cur.wait_stream(st)

@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
     ap.add_argument("--playouts", type=int, default=1000)
     ap.add_argument("--leaves", type=int, default=64, help="leaves per game per wave (virtual loss)")
+    ap.add_argument("--streams", type=int, default=4, help="sub-batches of games on separate CUDA streams")
     ap.add_argument("--c-puct", type=float, default=5.0)
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -166,7 +167,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from alphazero_quoridor_b200 import _lib
-    from alphazero_quoridor_b200.selfplay import BatchedSelfPlay
+    from alphazero_quoridor_b200.selfplay import StreamedSelfPlay
     from alphazero_quoridor_b200.tree import RolloutEvaluator
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,26 +186,45 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
-    ev = RolloutEvaluator(seed=args.seed, limit=1000)
-    sp = BatchedSelfPlay(args.games, ev, c_puct=args.c_puct, n_playout=args.playouts, leaves_per_game=args.leaves,
-                         pure=True, seed=args.seed, game_id_base=rank * args.games, device=dev)
-    m = sp.mcts
-    m.count_tree_steps = True
     from alphazero_quoridor_b200.rollout import workspace_words
-    ws = torch.zeros(workspace_words(args.games * args.leaves), dtype=torch.int64, device=dev)   # word 1: cumulative plies
-    ev._ws = ws
-    # time every rollout launch on its stream (roofline of the dominant kernel)
-    roll_events = []
-    orig_eval = ev.evaluate
+    per_stream = args.games // args.streams
+    roll_events = []          # (start, end, n_rollouts) of every rollout launch (roofline of the dominant kernel)
+    evaluators = []
 
-    def timed_eval(mcts, leaf_states, masks, rids):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        out = orig_eval(mcts, leaf_states, masks, rids)
-        b.record()
-        roll_events.append((a, b, leaf_states.shape[0]))
-        return out
-    ev.evaluate = timed_eval
+    def make_evaluator():
+        ev = RolloutEvaluator(seed=args.seed, limit=1000)
+        ev._ws = torch.zeros(workspace_words(per_stream * args.leaves), dtype=torch.int64, device=dev)   # word 1: plies
+        orig = ev.evaluate
+
+        def timed_eval(mcts, leaf_states, masks, rids):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = orig(mcts, leaf_states, masks, rids)
+            b.record()
+            roll_events.append((a, b, leaf_states.shape[0]))
+            return out
+        ev.evaluate = timed_eval
+        evaluators.append(ev)
+        return ev
+
+    sp = StreamedSelfPlay(args.games, make_evaluator, n_streams=args.streams, c_puct=args.c_puct,
+                          n_playout=args.playouts, leaves_per_game=args.leaves, pure=True, seed=args.seed,
+                          game_id_base=rank * args.games, device=dev)
+    engines = [s.mcts for s in sp.subs]
+    for m in engines:
+        m.count_tree_steps = True
+
+    def rollout_plies():
+        return sum(int(ev._ws[1].item()) for ev in evaluators)
+
+    def tree_steps():
+        return sum(int(m.tree_steps.item()) for m in engines)
+
+    def zero_counters():
+        for ev in evaluators:
+            ev._ws[1] = 0
+        for m in engines:
+            m.tree_steps.zero_()
 
     def barrier():
         if world > 1:
@@ -215,8 +235,7 @@ def run_ours(args):
         sp.step()
     barrier()
     roll_events.clear()
-    ws[1] = 0
-    m.tree_steps.zero_()
+    zero_counters()
     moves0 = sp.moves_played
     launches0 = _lib.LAUNCHES
     clocks = ClockSampler(local)
@@ -232,7 +251,7 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clk = clocks.stop() if rank == 0 else None
     launches = _lib.LAUNCHES - launches0
-    env_steps = int(ws[1].item()) + int(m.tree_steps.item()) + (sp.moves_played - moves0)
+    env_steps = rollout_plies() + tree_steps() + (sp.moves_played - moves0)
     playouts = args.games * args.playouts * args.steps
     roll_ms = [a.elapsed_time(b) for a, b, _ in roll_events]
     roll_n = [n for _, _, n in roll_events]
@@ -243,33 +262,47 @@ def run_ours(args):
     host_states = torch.empty((args.games, 3), dtype=torch.int64).pin_memory()
     host_moves = torch.empty((args.games,), dtype=torch.int32).pin_memory()
     host_visits = torch.empty((args.games, 140), dtype=torch.int32).pin_memory()
-    host_states.copy_(m.root_state)
+    host_states.copy_(torch.cat([m.root_state for m in engines], 0))
+    start_row = sp.subs[0]._start.cpu()[0]
     torch.cuda.synchronize()
-    ws[1] = 0
-    m.tree_steps.zero_()
+    zero_counters()
     e2e_steps = max(1, min(args.steps, 2))
     barrier()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    cur = torch.cuda.current_stream(dev)
     t0.record()
     for _ in range(e2e_steps):
-        dstates = host_states.to(dev, non_blocking=True)
-        m.reset(dstates)
-        m.search()
-        visits, _, _ = m.root_stats(temp=1.0)
-        moves = m.choose(mode=0)
-        m.advance(moves, keep_subtree=False)
-        host_moves.copy_(moves, non_blocking=True)
-        host_visits.copy_(visits, non_blocking=True)
-        host_states.copy_(m.root_state, non_blocking=True)
+        for st in sp.streams:
+            st.wait_stream(cur)
+        for i, (sub, st) in enumerate(zip(sp.subs, sp.streams)):
+            with torch.cuda.stream(st):
+                lo, hi = i * per_stream, (i + 1) * per_stream
+                sub.mcts.reset(host_states[lo:hi].to(dev, non_blocking=True))
+        plans = [sub.wave_plan() for sub in sp.subs]
+        for w in range(max(len(p) for p in plans)):
+            for sub, st, plan in zip(sp.subs, sp.streams, plans):
+                if w < len(plan):
+                    with torch.cuda.stream(st):
+                        sub.mcts.playout_wave(plan[w])
+        for i, (sub, st) in enumerate(zip(sp.subs, sp.streams)):
+            with torch.cuda.stream(st):
+                lo, hi = i * per_stream, (i + 1) * per_stream
+                m = sub.mcts
+                visits, _, _ = m.root_stats(temp=1.0)
+                moves = m.choose(mode=0)
+                m.advance(moves, keep_subtree=False)
+                host_moves[lo:hi].copy_(moves, non_blocking=True)
+                host_visits[lo:hi].copy_(visits, non_blocking=True)
+                host_states[lo:hi].copy_(m.root_state, non_blocking=True)
         torch.cuda.synchronize()
         # finished games restart on the host side of the boundary
         done = ((host_states[:, 2] >> 40) & 1).bool()
         if bool(done.any()):
-            host_states[done] = sp._start.cpu()[0]
+            host_states[done] = start_row
     t1.record()
     barrier()
     e2e_ms = t0.elapsed_time(t1)
-    e2e_env = int(ws[1].item()) + int(m.tree_steps.item()) + args.games * e2e_steps
+    e2e_env = rollout_plies() + tree_steps() + args.games * e2e_steps
     e2e_ms, (e2e_env,) = reduce_stats(e2e_ms, [e2e_env], device=dev)
     h2d = args.games * 24
     d2h = args.games * (4 + 140 * 4 + 24)
@@ -297,8 +330,10 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args), "games_per_gpu": args.games, "playouts_per_move": args.playouts,
-                   "leaves_per_game_per_wave": args.leaves, "parallelism": "games sharded by index x%d, no collective" % world,
-                   "l2": "inputs larger than L2: tree arenas %.1f GB/GPU; rollouts are register resident" % (m.nbytes() / 1e9)},
+                   "leaves_per_game_per_wave": args.leaves, "cuda_streams": args.streams,
+                   "parallelism": "games sharded by index x%d, no collective" % world,
+                   "l2": "inputs larger than L2: tree arenas %.1f GB/GPU; rollouts are register resident"
+                         % (sum(m.nbytes() for m in engines) / 1e9)},
         "mcts_sims_per_s": playouts_total / (ms * 1e-3),
         "moves_per_s": args.games * world * args.steps / (ms * 1e-3),
         "env_steps_per_playout": env_total / playouts_total,

@@ -250,3 +250,34 @@ def test_full_size_properties(qz):
     _, want = O.sweeps(np.array([d["H"] for d in hs], dtype=np.uint64), np.array([d["V"] for d in hs], dtype=np.uint64),
                        _meta5(hs))
     assert np.array_equal(_u64(m3[idx].cpu().numpy()), want)
+
+
+def test_stuck_rollouts_vs_oracle(qz):
+    """Late positions where a player still owns walls but (nearly) none can be placed legally: these rollouts
+    leave the per-lane kernel and run in the block-per-rollout kernel with memoised backward floods
+    (qz_rollout_stuck_kernel).  Same Philox streams => value, plies and final position equal the oracle's."""
+    from alphazero_quoridor_b200.rollout import rollout
+    from alphazero_quoridor_b200.synthetic import midgame_positions
+    pos = midgame_positions(60000, seed=123, min_plies=28, max_plies=70)
+    meta = pos[:, 2]
+    walls = ((meta >> 16) & 0xFF) + ((meta >> 24) & 0xFF)
+    live = ((meta >> 40) & 1) == 0
+    sel = (walls > 0) & live
+    stuck = pos[sel][:160].contiguous()
+    assert stuck.shape[0] >= 60, "need late positions with walls in hand"
+    seed = 4242
+    res, plies, final = rollout(stuck, per_state=1, seed=seed, rid_base=9000, limit=1000, return_final=True)
+    res, plies = res.cpu().numpy(), plies.cpu().numpy()
+    fin = qz.BatchedQuoridor(final.shape[0], states=final).host_states()
+    src = qz.BatchedQuoridor(stuck.shape[0], states=stuck).host_states()
+    n_long = 0
+    for r, d in enumerate(src):
+        g = O.OracleGame().set_position(d["H"], d["V"], d["p1"], d["p2"], d["w1"], d["w2"], d["cur"])
+        v, k = g.rollout(seed, 9000 + r, 1000)
+        pos_o = g.position()
+        f = fin[r]
+        assert (int(res[r]), int(plies[r])) == (v, k), r
+        assert (f["H"], f["V"], f["p1"], f["p2"], f["w1"], f["w2"], f["cur"]) == (
+            pos_o["H"], pos_o["V"], pos_o["p1"], pos_o["p2"], pos_o["w1"], pos_o["w2"], pos_o["cur"])
+        n_long += (f["w1"] + f["w2"]) > 0          # still holding walls at the end: stuck all the way
+    assert n_long >= 10
