@@ -35,7 +35,9 @@ SIGNATURES = {
     "qz_env_legal_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
     "qz_env_encode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _i64, _vp]),
     "qz_rollout_workspace_bytes": (C.c_int64, [_i64]),
-    "qz_rollout": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qz_rollout": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "qz_rollout_finish": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "qz_mcts_backup_pending": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "qz_mcts_init": (C.c_int, [_vp, _vp, _vp, _vp]),
     "qz_mcts_select": (C.c_int, [_vp, _f64, C.c_int, C.c_int, _vp]),
     "qz_mcts_expand_backup": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),

@@ -179,10 +179,14 @@ __global__ void __launch_bounds__(128) qz_mcts_expand_backup_kernel(qz_tree t, Q
         const int node_cb = child_base[node];
         __syncwarp();
         double v;
+        bool pending = false;
         if (flags & QZ_LEAF_TERMINAL) {
             v = a.fix_terminal_sign ? -1.0 : 1.0;                       // mcts.py:125 (mover not rotated => +1)
         } else {
             v = a.value_f64 ? a.value_f64[L] : (a.value_f32 ? (double)a.value_f32[L] : (double)a.value_i8[L]);
+            // a rollout still running in the deferred pass: expand now, back up later (qz_mcts_backup_pending);
+            // the path keeps its in-flight marks meanwhile
+            pending = a.value_i8 && a.value_i8[L] == (int8_t)QZ_ROLLOUT_PENDING;
             if (node_cb < 0 && !(flags & QZ_LEAF_DEPTH_OVERFLOW)) {
                 uint32_t pawn; uint64_t hl, vl;
                 const uint64_t mk[3] = {a.mask3[3 * L], a.mask3[3 * L + 1], a.mask3[3 * L + 2]};
@@ -218,6 +222,11 @@ __global__ void __launch_bounds__(128) qz_mcts_expand_backup_kernel(qz_tree t, Q
             }
         }
         __syncwarp();
+        if (pending) {
+            if (lane == 0) t.leaf_flags[L] = (uint8_t)(flags | QZ_LEAF_PENDING);
+            __syncwarp();
+            continue;
+        }
         if (lane == 0) {
             const int32_t *path = t.path + L * t.max_depth;
             const int len = t.path_len[L];
@@ -252,6 +261,49 @@ extern "C" int qz_mcts_expand_backup(const qz_tree *tree, const uint64_t *mask3,
     a.fix_terminal_sign = fix_terminal_sign; a.overflow_count = overflow_count;
     qz_mcts_expand_backup_kernel<<<qz_blocks_for(tree->n_games, 4), 128, 0, (cudaStream_t)stream>>>(*tree, a);
     return qz_check_launch("qz_mcts_expand_backup");
+}
+
+// Back up the leaves whose rollout was deferred (QZ_LEAF_PENDING) once their values are known.  One thread per
+// game, its pending leaves in order; same arithmetic as qz_mcts_expand_backup_kernel.
+__global__ void qz_mcts_backup_pending_kernel(qz_tree t, const int8_t *__restrict__ value_i8, int fix_terminal_sign) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= t.n_games) return;
+    const int64_t o = g * t.node_cap;
+    int32_t *__restrict__ visits = t.visits + o;
+    double *__restrict__ q = t.q + o;
+    uint32_t *__restrict__ meta = t.node_meta + o;
+    const int K = t.leaves_per_game;
+    const int root = t.root[g];
+    for (int k = 0; k < K; k++) {
+        const int64_t L = g * K + k;
+        const unsigned flags = t.leaf_flags[L];
+        if (!(flags & QZ_LEAF_PENDING)) continue;
+        const double v = (flags & QZ_LEAF_TERMINAL) ? (fix_terminal_sign ? -1.0 : 1.0) : (double)value_i8[L];
+        const int32_t *path = t.path + L * t.max_depth;
+        const int len = t.path_len[L];
+        double x = -v;
+        for (int d = len - 1; d >= 0; d--) {
+            const int nd = path[d];
+            const int nv = visits[nd] + 1;
+            visits[nd] = nv;
+            const double qo = q[nd];
+            q[nd] = qo + 1.0 * (x - qo) / (double)nv;
+            if (d > 0) meta[nd] -= (1u << 16);
+            x = -x;
+        }
+        meta[root] -= (1u << 16);
+        t.leaf_flags[L] = (uint8_t)(flags & ~QZ_LEAF_PENDING);
+    }
+}
+
+extern "C" int qz_mcts_backup_pending(const qz_tree *tree, const int8_t *value_i8, int fix_terminal_sign, void *stream) {
+    int rc = qz_tree_check(tree, "qz_mcts_backup_pending");
+    if (rc) return rc;
+    QZ_REQUIRE_PTR(value_i8);
+    if (tree->n_games == 0) return 0;
+    qz_mcts_backup_pending_kernel<<<qz_blocks_for(tree->n_games, 128), 128, 0, (cudaStream_t)stream>>>(*tree, value_i8,
+                                                                                                       fix_terminal_sign);
+    return qz_check_launch("qz_mcts_backup_pending");
 }
 
 // ------------------------------------------------------------------------------------------ root statistics

@@ -27,7 +27,9 @@ struct QzRolloutArgs {
     int32_t *plies;                // nullable [n_rollouts]
     qz_state *final_states;        // nullable [n_rollouts]
     unsigned long long *counter;   // [0] wall-phase work counter, [1] cumulative plies, [2] pawn-phase work counter,
-                                   // [3] number of ejected ("stuck") rollouts, [4] stuck-phase work counter
+                                   // [3] number of ejected ("stuck") rollouts, [4] stuck-phase work counter,
+                                   // [5] pawn-phase work counter of the deferred pass
+    int32_t list_mode;             // pawn kernel: 0 = all rollouts, 1 = only those of stuck_list (deferred pass)
     qz_state *mid;                 // [n_rollouts] state when a rollout leaves a phase
     int32_t *stuck_list;           // [n_rollouts] rollouts ejected from the wall phase
 };
@@ -93,6 +95,7 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
                 if (act == -2) {                                        // stuck: hand over to the block-per-rollout kernel
                     const unsigned long long k = atomicAdd(a.counter + 3, 1ull);
                     a.stuck_list[k] = (int32_t)r;
+                    s.meta |= (uint64_t)QZ_FLAG_PENDING << 40;
                     leave = true;
                 } else if (act < 0) {
                     s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40;
@@ -133,6 +136,7 @@ __global__ void __launch_bounds__(QZ_STUCK_THREADS, 4) qz_rollout_stuck_kernel(Q
         const int64_t r = sh_entry;
         if (r < 0) break;
         QzState s = qz_load_state(a.mid + r);
+        s.meta &= ~((uint64_t)QZ_FLAG_PENDING << 40);
         const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, r)) + 2);
         int steps = (int)qz_ply(s.meta) - (int)qz_ply(m0);
         QzRng rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + r) : a.rid_base + (uint64_t)r);
@@ -207,8 +211,10 @@ __global__ void __launch_bounds__(128) qz_rollout_pawn_kernel(QzRolloutArgs a) {
     ctx = qz_ctx_build(0, 0);
     for (;;) {
         const bool want = (r < 0) && !exhausted;
-        const int64_t got = qz_claim(a.counter + 2, want, a.n_rollouts);
+        int64_t got = qz_claim(a.list_mode ? a.counter + 5 : a.counter + 2, want,
+                               a.list_mode ? (int64_t)a.counter[3] : a.n_rollouts);
         if (want) {
+            if (got >= 0 && a.list_mode) got = a.stuck_list[got];
             if (got >= 0) {
                 r = got;
                 s = qz_load_state(a.mid + r);
@@ -222,6 +228,10 @@ __global__ void __launch_bounds__(128) qz_rollout_pawn_kernel(QzRolloutArgs a) {
             }
         }
         if (__all_sync(QZ_FULL_MASK, r < 0)) break;
+        if (r >= 0 && (qz_flags(s.meta) & QZ_FLAG_PENDING)) {
+            a.result[r] = (int8_t)-128;            // deferred: finished later by qz_rollout_finish
+            r = -1;
+        }
         if (r >= 0) {
             const unsigned fl = qz_flags(s.meta);
             bool finished = (fl & (QZ_FLAG_DONE | QZ_FLAG_STALEMATE)) || steps >= a.limit - 1 ||
@@ -273,37 +283,69 @@ static int qz_persistent_blocks(const void *kernel, int64_t n_items, int items_p
     return (int)(blocks < needed ? blocks : needed);
 }
 
-extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
-                          int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
-                          int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, void *stream) {
-    QZ_REQUIRE(n_rollouts >= 0 && n_states >= 0 && limit >= 1);
+static int qz_rollout_args(QzRolloutArgs &a, const qz_state *states, int64_t n_states, const int32_t *state_index,
+                           int32_t per_state, int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids,
+                           int32_t limit, int8_t *result, int32_t *plies, qz_state *final_states, void *workspace,
+                           const char *fn) {
+    if (!(n_rollouts >= 0 && n_states >= 0 && limit >= 1)) return qz_fail(QZ_E_RANGE, "%s: bad sizes", fn);
     if (n_rollouts == 0) return 0;
-    QZ_REQUIRE_PTR(states);
-    QZ_REQUIRE_PTR(result);
-    QZ_REQUIRE_PTR(workspace);
-    QZ_REQUIRE_ALIGN(states, 8);
-    QZ_REQUIRE_ALIGN(workspace, 8);
-    QZ_REQUIRE_ALIGN(final_states, 8);
-    if (state_index == nullptr) QZ_REQUIRE(per_state >= 1 && n_rollouts <= n_states * (int64_t)per_state);
-    cudaStream_t st = (cudaStream_t)stream;
-    unsigned long long *ctr = (unsigned long long *)workspace;
-    cudaError_t e = cudaMemsetAsync(ctr, 0, 8, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(ctr + 2, 0, 24, st);
-    if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout: memset: %s", cudaGetErrorString(e));
-    QzRolloutArgs a;
+    if (!states || !result || !workspace) return qz_fail(QZ_E_NULL, "%s: states / result / workspace is NULL", fn);
+    if (((uintptr_t)states | (uintptr_t)workspace | (uintptr_t)final_states) % 8)
+        return qz_fail(QZ_E_ALIGN, "%s: states / workspace / final_states not 8-byte aligned", fn);
+    if (state_index == nullptr && !(per_state >= 1 && n_rollouts <= n_states * (int64_t)per_state))
+        return qz_fail(QZ_E_RANGE, "%s: per_state does not cover n_rollouts", fn);
     a.states = states; a.state_index = state_index; a.rids = rids; a.rid_base = rid_base; a.seed = seed;
     a.n_rollouts = n_rollouts; a.per_state = per_state > 0 ? per_state : 1; a.limit = limit;
     a.result = result; a.plies = plies; a.final_states = final_states;
-    a.counter = ctr;
+    a.counter = (unsigned long long *)workspace;
+    a.list_mode = 0;
     a.mid = (qz_state *)((char *)workspace + 64);
     a.stuck_list = (int32_t *)((char *)workspace + 64 + n_rollouts * (int64_t)sizeof(qz_state));
+    return 0;
+}
+
+extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
+                          int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
+                          int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, int32_t flags,
+                          void *stream) {
+    QzRolloutArgs a;
+    int rc = qz_rollout_args(a, states, n_states, state_index, per_state, n_rollouts, seed, rid_base, rids, limit, result,
+                             plies, final_states, workspace, "qz_rollout");
+    if (rc || n_rollouts == 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(a.counter, 0, 8, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.counter + 2, 0, 32, st);
+    if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout: memset: %s", cudaGetErrorString(e));
     qz_rollout_wall_kernel<<<qz_persistent_blocks((const void *)qz_rollout_wall_kernel, n_rollouts, 128), 128, 0, st>>>(a);
-    int rc = qz_check_launch("qz_rollout (wall phase)");
+    rc = qz_check_launch("qz_rollout (wall phase)");
     if (rc) return rc;
-    // the number of ejected rollouts is only known on the device: launch a resident grid, blocks exit when the list is empty
-    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1), QZ_STUCK_THREADS, 0, st>>>(a);
-    rc = qz_check_launch("qz_rollout (stuck phase)");
-    if (rc) return rc;
+    if (!(flags & QZ_ROLLOUT_DEFER_STUCK)) {
+        // the number of ejected rollouts is only known on the device: launch a resident grid, blocks exit when the list is empty
+        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1), QZ_STUCK_THREADS, 0, st>>>(a);
+        rc = qz_check_launch("qz_rollout (stuck phase)");
+        if (rc) return rc;
+    }
     qz_rollout_pawn_kernel<<<qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, 128), 128, 0, st>>>(a);
     return qz_check_launch("qz_rollout (pawn phase)");
+}
+
+// The deferred pass of qz_rollout(..., QZ_ROLLOUT_DEFER_STUCK): same arguments and buffers.
+extern "C" int qz_rollout_finish(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
+                                 int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
+                                 int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, void *stream) {
+    QzRolloutArgs a;
+    int rc = qz_rollout_args(a, states, n_states, state_index, per_state, n_rollouts, seed, rid_base, rids, limit, result,
+                             plies, final_states, workspace, "qz_rollout_finish");
+    if (rc || n_rollouts == 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(a.counter + 4, 0, 16, st);
+    if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout_finish: memset: %s", cudaGetErrorString(e));
+    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1), QZ_STUCK_THREADS, 0, st>>>(a);
+    rc = qz_check_launch("qz_rollout_finish (stuck phase)");
+    if (rc) return rc;
+    a.list_mode = 1;
+    // the deferred list is short (well under 1 % of the rollouts): a quarter of a resident wave is plenty
+    int blocks = qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, 128) / 4;
+    qz_rollout_pawn_kernel<<<blocks > 0 ? blocks : 1, 128, 0, st>>>(a);
+    return qz_check_launch("qz_rollout_finish (pawn phase)");
 }

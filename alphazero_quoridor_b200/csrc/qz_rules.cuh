@@ -39,6 +39,7 @@ struct QzState {
 #define QZ_FLAG_STALEMATE 0x08u     // mover has no legal action (reference: actions()==[] then crashes)
 #define QZ_FLAG_TRUNCATED 0x10u     // ply cap hit (engine-side cap; reference loops forever)
 #define QZ_FLAG_ILLEGAL 0x20u       // safe-mode step rejected the action (quoridor.py:167-169)
+#define QZ_FLAG_PENDING 0x40u       // rollout scratch only: parked for the stuck-rollout kernel (never in user states)
 
 QZ_HD int qz_p1(uint64_t m) { return (int)(int8_t)(m & 0xFF); }
 QZ_HD int qz_p2(uint64_t m) { return (int)(int8_t)((m >> 8) & 0xFF); }

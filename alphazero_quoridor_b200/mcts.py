@@ -57,10 +57,11 @@ class _CallbackEvaluator:
     def __init__(self, fn):
         self.fn = fn
 
-    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
+    def evaluate(self, mcts, lset, leaf_rids):
+        leaf_states = lset.leaf_state
         m = leaf_states.shape[0]
         rows = leaf_states.cpu().numpy()
-        flags = mcts.leaf_flags.cpu().numpy()
+        flags = lset.leaf_flags.cpu().numpy()
         priors = np.zeros((m, 140), dtype=np.float32)
         values = np.zeros((m,), dtype=np.float64)
         for i in range(m):

@@ -19,7 +19,7 @@ import torch
 from . import _lib
 from .rollout import rollout as _rollout
 
-LEAF_TERMINAL, LEAF_DEPTH_OVERFLOW, LEAF_ARENA_OVERFLOW, LEAF_DUPLICATE, LEAF_INACTIVE = 1, 2, 4, 8, 16
+LEAF_TERMINAL, LEAF_DEPTH_OVERFLOW, LEAF_ARENA_OVERFLOW, LEAF_DUPLICATE, LEAF_INACTIVE, LEAF_PENDING = 1, 2, 4, 8, 16, 32
 MAX_CHILDREN = 140
 
 
@@ -52,6 +52,20 @@ class _Arena:
 
 
 # ------------------------------------------------------------------------------------------------ evaluators
+class _LeafSet:
+    """The per-wave leaf arrays of struct qz_tree.  A search that defers stuck rollouts keeps several sets in
+    flight (the select of wave w+1 must not overwrite the paths wave w's deferred backups still need)."""
+
+    def __init__(self, m, max_depth, dev):
+        self.leaf_node = torch.empty(m, dtype=torch.int32, device=dev)
+        self.leaf_state = torch.zeros((m, 3), dtype=torch.int64, device=dev)
+        self.path = torch.empty(m * max_depth, dtype=torch.int32, device=dev)
+        self.path_len = torch.empty(m, dtype=torch.int32, device=dev)
+        self.leaf_flags = torch.zeros(m, dtype=torch.uint8, device=dev)
+        self.leaf_mask = torch.zeros((m, 3), dtype=torch.int64, device=dev)
+        self.owed = None            # evaluator state of a deferred wave (None = nothing owed)
+
+
 class StubEvaluator:
     """Parity stubs evaluated by the qz_stub_eval kernel.  kind: 1 = S1 uniform, 2 = S2 hash, 3 = S3 hash/8."""
 
@@ -59,39 +73,62 @@ class StubEvaluator:
         self.kind = {"S1": 1, "S2": 2, "S3": 3}.get(kind, kind)
         self._buf = None
 
-    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
-        m = leaf_states.shape[0]
+    def evaluate(self, mcts, lset, leaf_rids):
+        m = lset.leaf_state.shape[0]
         if self._buf is None or self._buf[0].shape[0] != m:
-            self._buf = (torch.empty((m, 140), dtype=torch.float32, device=leaf_states.device),
-                         torch.empty((m,), dtype=torch.float64, device=leaf_states.device))
+            self._buf = (torch.empty((m, 140), dtype=torch.float32, device=lset.leaf_state.device),
+                         torch.empty((m,), dtype=torch.float64, device=lset.leaf_state.device))
         priors, values = self._buf
-        _lib.check(mcts.lib.qz_stub_eval(_lib.ptr(leaf_states), _lib.ptr(masks), self.kind, _lib.ptr(priors),
+        _lib.check(mcts.lib.qz_stub_eval(_lib.ptr(lset.leaf_state), _lib.ptr(lset.leaf_mask), self.kind, _lib.ptr(priors),
                                          _lib.ptr(values), m, mcts._stream()), "qz_stub_eval")
         return dict(priors=priors, value_f64=values)
 
 
 class RolloutEvaluator:
-    """pure_mcts.policy_value_fn + _evaluate_rollout: uniform priors, value = random playout (<= limit-1 plies)."""
+    """pure_mcts.policy_value_fn + _evaluate_rollout: uniform priors, value = random playout (<= limit-1 plies).
+
+    With `defer_stuck` (used by BatchedMCTS(defer_depth >= 2)) the few stuck rollouts of a wave are finished on a
+    side stream while later waves run; their leaves are expanded at once and backed up when the result is in."""
 
     uniform_prior = True
+    can_defer = True
 
     def __init__(self, seed=0, limit=1000):
         self.seed, self.limit = seed, limit
-        self.env_steps = 0
-        self.count_steps = False
-        self._ws = None
+        self._per_set = {}
 
-    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
-        if self._ws is None:
+    def _buffers(self, lset):
+        b = self._per_set.get(id(lset))
+        if b is None:
             from .rollout import workspace_words
-            self._ws = torch.zeros((workspace_words(leaf_states.shape[0]),), dtype=torch.int64,
-                                   device=leaf_states.device)
-        res, plies, _ = _rollout(leaf_states, seed=self.seed, rids=leaf_rids,
-                                 state_index=mcts._leaf_iota, limit=self.limit,
-                                 return_plies=self.count_steps, workspace=self._ws)
-        if self.count_steps:
-            self.env_steps = self.env_steps + plies.sum(dtype=torch.int64)
-        return dict(priors=None, value_i8=res)
+            m, dev = lset.leaf_state.shape[0], lset.leaf_state.device
+            b = dict(ws=torch.zeros((workspace_words(m),), dtype=torch.int64, device=dev),
+                     result=torch.empty((m,), dtype=torch.int8, device=dev))
+            self._per_set[id(lset)] = b
+        return b
+
+    def plies_played(self):
+        """Total rollout plies so far (sums the cumulative counters of the workspaces; synchronises)."""
+        return sum(int(b["ws"][1].item()) for b in self._per_set.values())
+
+    def zero_plies(self):
+        for b in self._per_set.values():
+            b["ws"][1] = 0
+
+    def evaluate(self, mcts, lset, leaf_rids, defer=False):
+        b = self._buffers(lset)
+        _rollout(lset.leaf_state, seed=self.seed, rids=leaf_rids, state_index=mcts._leaf_iota, limit=self.limit,
+                 return_plies=False, workspace=b["ws"], result=b["result"], defer_stuck=defer)
+        if defer:
+            lset.owed = dict(rids=leaf_rids)
+        return dict(priors=None, value_i8=b["result"])
+
+    def finish(self, mcts, lset):
+        """The deferred pass of `evaluate(..., defer=True)` for this leaf set (call on the side stream)."""
+        b = self._buffers(lset)
+        _rollout(lset.leaf_state, seed=self.seed, rids=lset.owed["rids"], state_index=mcts._leaf_iota,
+                 limit=self.limit, return_plies=False, workspace=b["ws"], result=b["result"], finish=True)
+        return b["result"]
 
 
 class NetEvaluator:
@@ -101,15 +138,15 @@ class NetEvaluator:
     def __init__(self, net):
         self.net = net
 
-    def evaluate(self, mcts, leaf_states, masks, leaf_rids):
-        probs, value = self.net.evaluate_states(leaf_states)
+    def evaluate(self, mcts, lset, leaf_rids):
+        probs, value = self.net.evaluate_states(lset.leaf_state)
         return dict(priors=probs, value_f32=value)
 
 
 # ------------------------------------------------------------------------------------------------ the search
 class BatchedMCTS:
     def __init__(self, n_games, evaluator, c_puct=5, n_playout=100, leaves_per_game=1, node_cap=None,
-                 max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None):
+                 max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None, defer_depth=0):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda")
@@ -132,12 +169,15 @@ class BatchedMCTS:
             self.arenas.append(_Arena(self.n, self.node_cap, dev))
         self.cur = 0
         m = self.n * self.K
-        self.leaf_node = torch.empty(m, dtype=torch.int32, device=dev)
-        self.leaf_state = torch.zeros((m, 3), dtype=torch.int64, device=dev)
-        self.path = torch.empty(m * self.max_depth, dtype=torch.int32, device=dev)
-        self.path_len = torch.empty(m, dtype=torch.int32, device=dev)
-        self.leaf_flags = torch.zeros(m, dtype=torch.uint8, device=dev)
-        self.leaf_mask = torch.zeros((m, 3), dtype=torch.int64, device=dev)
+        # deferred evaluation (stuck rollouts finished on a side stream while later waves run): wave w's owed
+        # backups are applied just before wave w + defer_depth reuses its leaf set
+        self.defer_depth = int(defer_depth) if getattr(evaluator, "can_defer", False) else 0
+        self.sets = [_LeafSet(m, self.max_depth, dev) for _ in range(max(1, self.defer_depth))]
+        self.cur_set = 0
+        self.wave_index = 0
+        # one side stream per leaf set: the stuck passes of consecutive waves are latency-bound (a few hundred
+        # long-running blocks each) and must overlap each other, not only the main stream
+        self.side_streams = [torch.cuda.Stream(device=dev) for _ in self.sets] if self.defer_depth >= 2 else []
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self._leaf_iota = torch.arange(m, dtype=torch.int32, device=dev)
         self._k_of_leaf = (torch.arange(m, dtype=torch.int64, device=dev) % self.K)
@@ -148,24 +188,45 @@ class BatchedMCTS:
         self.total_playouts = 0
         self.count_tree_steps = False    # bench: accumulate the env steps replayed by the descents
         self.tree_steps = torch.zeros((), dtype=torch.int64, device=dev)
-        self._structs = [self._make_struct(a) for a in self.arenas]
+        self._structs = [[self._make_struct(a, ls) for ls in self.sets] for a in self.arenas]
 
     # ---- plumbing ----
     def _stream(self):
         return _lib.stream_ptr(self.device)
 
-    def _make_struct(self, a):
+    def _make_struct(self, a, ls):
         t = QzTree()
         t.n_games, t.node_cap, t.max_depth, t.leaves_per_game, t.reserved = self.n, self.node_cap, self.max_depth, self.K, 0
         for name in ("prior", "visits", "q", "child_base", "node_meta", "root", "n_nodes", "root_state"):
             setattr(t, name, getattr(a, name).data_ptr())
         for name in ("leaf_node", "leaf_state", "path", "path_len", "leaf_flags"):
-            setattr(t, name, getattr(self, name).data_ptr())
+            setattr(t, name, getattr(ls, name).data_ptr())
         return t
 
     @property
     def tree(self):
-        return self._structs[self.cur]
+        return self._structs[self.cur][self.cur_set]
+
+    # the leaf arrays of the most recent wave (read by callback evaluators and tests)
+    @property
+    def leaf_state(self):
+        return self.sets[self.cur_set].leaf_state
+
+    @property
+    def leaf_mask(self):
+        return self.sets[self.cur_set].leaf_mask
+
+    @property
+    def leaf_flags(self):
+        return self.sets[self.cur_set].leaf_flags
+
+    @property
+    def path_len(self):
+        return self.sets[self.cur_set].path_len
+
+    @property
+    def leaf_node(self):
+        return self.sets[self.cur_set].leaf_node
 
     @property
     def arena(self):
@@ -183,34 +244,67 @@ class BatchedMCTS:
         """Fresh trees (mcts.py:97 / update_with_move(-1)) rooted at `root_states` (int64 [n,3])."""
         root_states = root_states.to(self.device).contiguous()
         assert root_states.shape == (self.n, 3)
+        self.drain()
         with torch.cuda.device(self.device):
             _lib.check(self.lib.qz_mcts_init(C.byref(self.tree), _lib.ptr(root_states), _lib.ptr(select),
                                              self._stream()), "qz_mcts_init")
         self.playouts_done = 0
 
+    def _settle(self, idx):
+        """Apply the backups wave (self.sets[idx]) still owes: wait for its deferred rollouts, then back them up."""
+        ls = self.sets[idx]
+        if ls.owed is None:
+            return
+        torch.cuda.current_stream(self.device).wait_event(ls.owed["done"])
+        _lib.check(self.lib.qz_mcts_backup_pending(C.byref(self._structs[self.cur][idx]), _lib.ptr(ls.owed["result"]),
+                                                   int(self.fix_terminal_sign), self._stream()), "qz_mcts_backup_pending")
+        ls.owed = None
+
+    def drain(self):
+        """Settle every deferred wave (before reading statistics, choosing a move or re-rooting)."""
+        if self.defer_depth >= 2:
+            with torch.cuda.device(self.device):
+                for i in range(len(self.sets)):
+                    self._settle((self.cur_set + 1 + i) % len(self.sets))      # oldest first
+
     def playout_wave(self, k_leaves=None):
         """One wave: k_leaves playouts per game (mcts.py:103-127)."""
         k = self.K if k_leaves is None else int(k_leaves)
+        defer = self.defer_depth >= 2
         with torch.cuda.device(self.device):
             st = self._stream()
+            if defer:
+                self.cur_set = self.wave_index % len(self.sets)
+                self._settle(self.cur_set)          # the wave that used this leaf set defer_depth waves ago
+            ls = self.sets[self.cur_set]
             _lib.check(self.lib.qz_mcts_select(C.byref(self.tree), self.c_puct, int(self.uniform_prior), k, st),
                        "qz_mcts_select")
             m = self.n * self.K
             if self.count_tree_steps:
-                self.tree_steps += (self.path_len.clamp(min=1) - 1).sum()
-            _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(self.leaf_state), _lib.ptr(self.leaf_mask), m, st),
+                self.tree_steps += (ls.path_len.clamp(min=1) - 1).sum()
+            _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_mask), m, st),
                        "qz_env_legal_mask")
             # rollout / RNG stream of leaf (g,k): unique per (game, playout)
             rids = None
             if getattr(self.evaluator, "uniform_prior", False):
                 rids = (self.game_id.repeat_interleave(self.K) + (self.total_playouts + self._k_of_leaf))
-            ev = self.evaluator.evaluate(self, self.leaf_state, self.leaf_mask, rids)
+            ev = self.evaluator.evaluate(self, ls, rids, defer=True) if defer else self.evaluator.evaluate(self, ls, rids)
             _lib.check(self.lib.qz_mcts_expand_backup(
-                C.byref(self.tree), _lib.ptr(self.leaf_mask), _lib.ptr(ev.get("priors")),
+                C.byref(self.tree), _lib.ptr(ls.leaf_mask), _lib.ptr(ev.get("priors")),
                 _lib.ptr(ev.get("value_f32")), _lib.ptr(ev.get("value_f64")), _lib.ptr(ev.get("value_i8")),
                 int(self.fix_terminal_sign), _lib.ptr(self.overflow), st), "qz_mcts_expand_backup")
+            if defer:
+                # finish the stuck rollouts of this wave on the side stream while the next waves run
+                cur = torch.cuda.current_stream(self.device)
+                side = self.side_streams[self.cur_set]
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    ls.owed["result"] = self.evaluator.finish(self, ls)
+                    ls.owed["done"] = torch.cuda.Event()
+                    ls.owed["done"].record()
         self.playouts_done += k
         self.total_playouts += k
+        self.wave_index += 1
 
     def search(self, n_playout=None):
         """get_move_probs' loop (mcts.py:135-139): n_playout playouts for every game."""
@@ -222,11 +316,13 @@ class BatchedMCTS:
             k = 1 if self.playouts_done == 0 else min(self.K, total - done)
             self.playout_wave(k)
             done += k
+        self.drain()
 
     def root_stats(self, temp=1e-3, want_q=False):
         """(visits int32 [n,140], probs float64 [n,140], root_visits int32 [n][, q float64 [n,140]])
         -- mcts.py:141-144 scattered by action id."""
         dev = self.device
+        self.drain()
         visits = torch.empty((self.n, 140), dtype=torch.int32, device=dev)
         probs = torch.empty((self.n, 140), dtype=torch.float64, device=dev)
         rootn = torch.empty((self.n,), dtype=torch.int32, device=dev)
@@ -240,6 +336,7 @@ class BatchedMCTS:
     def choose(self, mode=0, temp=1e-3, seed=0, noise_eps=0.25, dir_alpha=0.3):
         """Moves int32 [n] (mcts.py:177-187 / pure_mcts.py:115).  mode 0 first-max visits, 1 sample from probs,
         2 sample from (1-eps)*probs + eps*Dirichlet(alpha)."""
+        self.drain()
         moves = torch.empty((self.n,), dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.qz_mcts_choose(C.byref(self.tree), int(mode), float(temp), float(noise_eps),
@@ -251,9 +348,10 @@ class BatchedMCTS:
         """update_with_move (mcts.py:146-151) for every game and step the root states by `moves`.
         keep_subtree=False (or a negative move) discards the tree (pure_mcts.py:142)."""
         moves = moves.to(device=self.device, dtype=torch.int32).contiguous()
+        self.drain()
         with torch.cuda.device(self.device):
             if keep_subtree and len(self.arenas) == 2:
-                src, dst = self._structs[self.cur], self._structs[1 - self.cur]
+                src, dst = self._structs[self.cur][self.cur_set], self._structs[1 - self.cur][self.cur_set]
                 _lib.check(self.lib.qz_mcts_reroot(C.byref(src), C.byref(dst), _lib.ptr(moves), 1, self._stream()),
                            "qz_mcts_reroot")
                 self.cur = 1 - self.cur

@@ -38,6 +38,7 @@ def parse():
     ap.add_argument("--playouts", type=int, default=1000)
     ap.add_argument("--leaves", type=int, default=64, help="leaves per game per wave (virtual loss)")
     ap.add_argument("--streams", type=int, default=4, help="sub-batches of games on separate CUDA streams")
+    ap.add_argument("--defer", type=int, default=3, help="waves a stuck rollout may lag behind (0 = finish in-wave)")
     ap.add_argument("--c-puct", type=float, default=5.0)
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -186,22 +187,20 @@ def run_ours(args):
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
 
-    from alphazero_quoridor_b200.rollout import workspace_words
     per_stream = args.games // args.streams
     roll_events = []          # (start, end, n_rollouts) of every rollout launch (roofline of the dominant kernel)
     evaluators = []
 
     def make_evaluator():
         ev = RolloutEvaluator(seed=args.seed, limit=1000)
-        ev._ws = torch.zeros(workspace_words(per_stream * args.leaves), dtype=torch.int64, device=dev)   # word 1: plies
         orig = ev.evaluate
 
-        def timed_eval(mcts, leaf_states, masks, rids):
+        def timed_eval(mcts, lset, rids, **kw):
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            out = orig(mcts, leaf_states, masks, rids)
+            out = orig(mcts, lset, rids, **kw)
             b.record()
-            roll_events.append((a, b, leaf_states.shape[0]))
+            roll_events.append((a, b, lset.leaf_state.shape[0]))
             return out
         ev.evaluate = timed_eval
         evaluators.append(ev)
@@ -209,20 +208,20 @@ def run_ours(args):
 
     sp = StreamedSelfPlay(args.games, make_evaluator, n_streams=args.streams, c_puct=args.c_puct,
                           n_playout=args.playouts, leaves_per_game=args.leaves, pure=True, seed=args.seed,
-                          game_id_base=rank * args.games, device=dev)
+                          game_id_base=rank * args.games, device=dev, defer_depth=args.defer)
     engines = [s.mcts for s in sp.subs]
     for m in engines:
         m.count_tree_steps = True
 
     def rollout_plies():
-        return sum(int(ev._ws[1].item()) for ev in evaluators)
+        return sum(ev.plies_played() for ev in evaluators)
 
     def tree_steps():
         return sum(int(m.tree_steps.item()) for m in engines)
 
     def zero_counters():
         for ev in evaluators:
-            ev._ws[1] = 0
+            ev.zero_plies()
         for m in engines:
             m.tree_steps.zero_()
 
@@ -288,6 +287,7 @@ def run_ours(args):
             with torch.cuda.stream(st):
                 lo, hi = i * per_stream, (i + 1) * per_stream
                 m = sub.mcts
+                m.drain()
                 visits, _, _ = m.root_stats(temp=1.0)
                 moves = m.choose(mode=0)
                 m.advance(moves, keep_subtree=False)
@@ -331,6 +331,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args), "games_per_gpu": args.games, "playouts_per_move": args.playouts,
                    "leaves_per_game_per_wave": args.leaves, "cuda_streams": args.streams,
+                   "stuck_rollout_defer_waves": args.defer,
                    "parallelism": "games sharded by index x%d, no collective" % world,
                    "l2": "inputs larger than L2: tree arenas %.1f GB/GPU; rollouts are register resident"
                          % (sum(m.nbytes() for m in engines) / 1e9)},

@@ -124,11 +124,21 @@ int qz_env_encode(const qz_state *states, void *out, int dtype, int layout, int 
  *                        plies played by every call (caller zeroes / reads it), i.e. the env-step count without a
  *                        per-rollout reduction; from byte 64 on, one qz_state per rollout parks the position between
  *                        the phases (wall, stuck, pawn: three kernels), followed by the list of ejected rollouts.
+ *   flags                QZ_ROLLOUT_DEFER_STUCK: the few rollouts ejected from the wall phase ("stuck": walls in hand
+ *                        but next to no legal placement, hundreds of serial plies) are NOT finished by this call;
+ *                        their result is QZ_ROLLOUT_PENDING (-128) until qz_rollout_finish, called later -- typically on
+ *                        another stream while the caller does other work -- with the SAME arguments and buffers, has
+ *                        run.  Results are identical either way.
  */
+#define QZ_ROLLOUT_DEFER_STUCK 1
+#define QZ_ROLLOUT_PENDING (-128)
 int64_t qz_rollout_workspace_bytes(int64_t n_rollouts);
 int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
                int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
-               int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, void *stream);
+               int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, int32_t flags, void *stream);
+int qz_rollout_finish(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
+                      int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
+                      int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Batched PUCT MCTS (mcts.py, pure_mcts.py).  n_games trees live in flat, caller-owned device arrays.
@@ -168,6 +178,7 @@ typedef struct qz_tree {
 #define QZ_LEAF_ARENA_OVERFLOW 0x04 /* children did not fit node_cap; leaf left unexpanded */
 #define QZ_LEAF_DUPLICATE 0x08      /* another leaf of the same wave expanded this node first */
 #define QZ_LEAF_INACTIVE 0x10       /* slot k >= k_leaves of this wave */
+#define QZ_LEAF_PENDING 0x20        /* value was QZ_ROLLOUT_PENDING: expanded, backup owed (qz_mcts_backup_pending) */
 
 /* MCTS.__init__ (mcts.py:89-100) / update_with_move(-1) (:150-151): fresh root (prior 1.0) for every game
  * (or only those with select[g] != 0); root_states (nullable) are copied into tree->root_state. */
@@ -189,6 +200,11 @@ int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_
 int qz_mcts_expand_backup(const qz_tree *tree, const uint64_t *mask3, const float *priors, const float *value_f32,
                           const double *value_f64, const int8_t *value_i8, int fix_terminal_sign,
                           int32_t *overflow_count, void *stream);
+
+/* Deferred half of qz_mcts_expand_backup: a leaf whose value_i8 was QZ_ROLLOUT_PENDING (its rollout is being
+ * finished by qz_rollout_finish) was expanded but not backed up and keeps its in-flight marks; this call backs up
+ * every such leaf of the tree's CURRENT leaf arrays with the now final value_i8 (update_recursive, mcts.py:44-62). */
+int qz_mcts_backup_pending(const qz_tree *tree, const int8_t *value_i8, int fix_terminal_sign, void *stream);
 
 /* get_move_probs (mcts.py:141-144): per game, root-child visit counts / Q scattered by action id into
  * [n,140] arrays (nullable each), softmax(1/temp*log(visits+1e-10)) in float64, and the root's own visits. */
