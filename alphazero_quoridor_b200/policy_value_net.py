@@ -167,7 +167,7 @@ class PolicyValueNet(object):
             v = value[0][0].cpu()
         return zip(legal_positions, act_probs[legal_positions]), v
 
-    def train_step(self, state_batch, mcts_probs, winner_batch, lr):
+    def train_step(self, state_batch, mcts_probs, winner_batch, lr, grad_hook=None):
         """policy_value_net.py:166-192: loss = (z - v)^2 - pi^T log p (+ weight decay via Adam)."""
         dev = self.device
         state_batch = torch.as_tensor(np.asarray(state_batch), dtype=torch.float32, device=dev)
@@ -181,6 +181,8 @@ class PolicyValueNet(object):
         policy_loss = -torch.mean(torch.sum(mcts_probs * log_act_probs, 1))
         loss = value_loss + policy_loss
         loss.backward()
+        if grad_hook is not None:
+            grad_hook()                         # e.g. NCCL all-reduce of the gradients (train.TrainPipeline)
         self.optimizer.step()
         entropy = -torch.mean(torch.sum(torch.exp(log_act_probs) * log_act_probs, 1))
         self._infer = None                      # inference copy is stale now

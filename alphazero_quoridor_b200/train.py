@@ -1,0 +1,137 @@
+"""Mirror of the reference's train.py (`TrainPipeline`, train.py:12-116) over the batched engine.
+
+Same hyper-parameter attributes and the same three methods (`collect_selfplay_data`, `policy_update`, `run`).
+Self-play is not one game at a time: `collect_selfplay_data(n)` advances `n_parallel_games` concurrent games
+(selfplay.BatchedSelfPlay, MCTS with the bf16 net on the device) until at least n of them have finished and
+appends their (state, mcts_probs, z) samples to the replay buffer.  A sample keeps the 24-byte game state, not
+the 26x9x9 float64 tensor of quoridor.py:589; `policy_update` re-encodes the minibatch with the encode kernel.
+
+SURVEY.md 8(f) lists the trainer as "next"; it is provided so that the self-play path has its real caller.  With
+torch.distributed initialised (one process per GPU, NCCL) gradients are averaged with an all-reduce per step --
+the only collective in the system -- and every rank collects its own shard of games.
+"""
+from __future__ import print_function
+
+import random
+from collections import deque
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .policy_value_net import PolicyValueNet
+from .quoridor import BatchedQuoridor
+from .selfplay import BatchedSelfPlay
+from .tree import NetEvaluator
+
+
+class TrainPipeline(object):
+    def __init__(self, init_model=None, n_parallel_games=256, leaves_per_game=4, device=None, seed=0,
+                 fix_terminal_sign=False, max_plies=600):
+        # train.py:17-31
+        self.learn_rate = 2e-3
+        self.lr_multiplier = 1.0
+        self.temp = 1.0
+        self.n_playout = 400
+        self.c_puct = 5
+        self.buffer_size = 10000
+        self.batch_size = 128
+        self.data_buffer = deque(maxlen=self.buffer_size)
+        self.play_batch_size = 1
+        self.epochs = 5
+        self.kl_targ = 0.02
+        self.check_freq = 50
+        self.game_batch_num = 1500
+        self.best_win_ratio = 0.0
+        self.pure_mcts_playout_num = 1000
+        self.policy_value_net = PolicyValueNet(model_file=init_model, device=device) if init_model else \
+            PolicyValueNet(device=device)
+        self.n_parallel_games = n_parallel_games
+        self.leaves_per_game = leaves_per_game
+        self.seed = seed
+        self.fix_terminal_sign = fix_terminal_sign
+        self.max_plies = max_plies
+        self._selfplay = None
+        self.episode_len = 0
+        self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _engine(self):
+        if self._selfplay is None or self._selfplay.mcts.n_playout != self.n_playout:
+            self._selfplay = BatchedSelfPlay(
+                self.n_parallel_games, NetEvaluator(self.policy_value_net), c_puct=self.c_puct,
+                n_playout=self.n_playout, leaves_per_game=self.leaves_per_game, temp=self.temp, pure=False,
+                seed=self.seed, game_id_base=self.rank * self.n_parallel_games, max_plies=self.max_plies,
+                record=True, fix_terminal_sign=self.fix_terminal_sign, device=self.policy_value_net.device)
+        return self._selfplay
+
+    def collect_selfplay_data(self, n_games=1, max_steps=100000):
+        """train.py:55-63: play until >= n_games more games have finished; extend the replay buffer."""
+        sp = self._engine()
+        target = len(sp.sink) + n_games
+        steps = 0
+        while len(sp.sink) < target and steps < max_steps:
+            sp.step()
+            steps += 1
+        finished, sp.sink = sp.sink, []
+        for st, pr, z in finished:
+            self.episode_len = st.shape[0]
+            st, pr, z = st.cpu(), pr.cpu(), z.cpu()
+            self.data_buffer.extend(zip(st.unbind(0), pr.unbind(0), z.tolist()))
+        return len(finished)
+
+    def _encode(self, state_rows):
+        rows = torch.stack(list(state_rows)).to(self.policy_value_net.device)
+        return BatchedQuoridor(rows.shape[0], states=rows, device=self.policy_value_net.device).encode(dtype=torch.float32)
+
+    def _sync_gradients(self):
+        if self.world > 1:
+            for p in self.policy_value_net.policy_value_net.parameters():
+                if p.grad is not None:
+                    dist.all_reduce(p.grad)
+                    p.grad /= self.world
+
+    def policy_update(self):
+        """train.py:65-92: <= 5 epochs on one minibatch, KL early stop, KL-adaptive learning-rate multiplier."""
+        mini_batch = random.sample(self.data_buffer, self.batch_size)
+        state_batch = self._encode([d[0] for d in mini_batch]).cpu().numpy()
+        mcts_probs_batch = np.stack([d[1].numpy() for d in mini_batch])
+        winner_batch = np.array([d[2] for d in mini_batch], dtype=np.float32)
+        old_probs, old_v = self.policy_value_net.policy_value(state_batch)
+        loss = entropy = kl = new_v = None
+        for i in range(self.epochs):
+            loss, entropy = self.policy_value_net.train_step(state_batch, mcts_probs_batch, winner_batch,
+                                                             self.learn_rate * self.lr_multiplier,
+                                                             grad_hook=self._sync_gradients)
+            new_probs, new_v = self.policy_value_net.policy_value(state_batch)
+            kl = np.mean(np.sum(old_probs * (np.log(old_probs + 1e-10) - np.log(new_probs + 1e-10)), axis=1))
+            if kl > self.kl_targ * 4:
+                break
+        if kl > self.kl_targ * 2 and self.lr_multiplier > 0.1:
+            self.lr_multiplier /= 1.5
+        elif kl < self.kl_targ / 2 and self.lr_multiplier < 10:
+            self.lr_multiplier *= 1.5
+        var = np.var(winner_batch)
+        self.last_stats = dict(kl=float(kl), lr_multiplier=self.lr_multiplier, loss=loss, entropy=entropy,
+                               explained_var_old=float(1 - np.var(winner_batch - old_v.flatten()) / var) if var > 0 else 0.0,
+                               explained_var_new=float(1 - np.var(winner_batch - new_v.flatten()) / var) if var > 0 else 0.0)
+        return loss, entropy
+
+    def run(self):
+        """train.py:94-111"""
+        try:
+            for i in range(self.game_batch_num):
+                self.collect_selfplay_data(self.play_batch_size)
+                if len(self.data_buffer) > self.batch_size:
+                    loss, entropy = self.policy_update()
+                    if self.rank == 0:
+                        with open('loss.txt', 'a') as f:
+                            f.writelines(str(loss) + '\n')
+                if (i + 1) % self.check_freq == 0 and self.rank == 0:
+                    self.policy_value_net.save_model('current_policy')
+        except KeyboardInterrupt:
+            print('\n\rquit')
+
+
+if __name__ == '__main__':
+    TrainPipeline().run()
