@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline micro-section")
+    ap.add_argument("--no-az", action="store_true", help="skip the AlphaZero-MCTS (BASELINE configs[2]) side measurement")
     return ap.parse_args()
 
 
@@ -189,6 +190,7 @@ def run_ours(args):
 
     per_stream = args.games // args.streams
     roll_events = []          # (start, end, n_rollouts) of every rollout launch (roofline of the dominant kernel)
+    stuck_events = []         # (start, end) of every deferred stuck-rollout pass (side streams)
     evaluators = []
 
     def make_evaluator():
@@ -203,6 +205,16 @@ def run_ours(args):
             roll_events.append((a, b, lset.leaf_state.shape[0]))
             return out
         ev.evaluate = timed_eval
+        orig_finish = ev.finish
+
+        def timed_finish(mcts, lset):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = orig_finish(mcts, lset)
+            b.record()
+            stuck_events.append((a, b))
+            return out
+        ev.finish = timed_finish
         evaluators.append(ev)
         return ev
 
@@ -234,6 +246,7 @@ def run_ours(args):
         sp.step()
     barrier()
     roll_events.clear()
+    stuck_events.clear()
     zero_counters()
     moves0 = sp.moves_played
     launches0 = _lib.LAUNCHES
@@ -254,6 +267,7 @@ def run_ours(args):
     playouts = args.games * args.playouts * args.steps
     roll_ms = [a.elapsed_time(b) for a, b, _ in roll_events]
     roll_n = [n for _, _, n in roll_events]
+    stuck_ms = [a.elapsed_time(b) for a, b in stuck_events]
     from alphazero_quoridor_b200.shard import reduce_stats
     ms, (env_total, playouts_total) = reduce_stats(ms, [env_steps, playouts], device=dev)   # max time, summed work
 
@@ -312,19 +326,25 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (qz_rollout_kernel): algorithmic HBM bytes per launch / its duration ----
-    # per rollout: 24 B start state + 4 B state index + 8 B stream id read, 1 B result written  
-    bytes_per_rollout = 24 + 4 + 8 + 1
-    avg_ms = sum(roll_ms) / max(len(roll_ms), 1)
+    # ---- roofline of the dominant kernels: the rollout launch = qz_rollout_{wall,pawn}_kernel on the main stream plus the
+    # deferred qz_rollout_stuck_kernel pass on a side stream.  Algorithmic HBM bytes per rollout: 24 B start state + 4 B
+    # state index + 8 B stream id read, 2 x 24 B through the phase hand-over buffer, 1 B result written.
+    bytes_per_rollout = 24 + 4 + 8 + 48 + 1
+    avg_main = sum(roll_ms) / max(len(roll_ms), 1)
+    avg_stuck = sum(stuck_ms) / max(len(stuck_ms), 1)
+    avg_ms = avg_main + avg_stuck
     avg_n = sum(roll_n) / max(len(roll_n), 1)
     achieved = bytes_per_rollout * avg_n / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    roofline = {"kernel": "qz_rollout_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+    roofline = {"kernel": "qz_rollout_wall_kernel + qz_rollout_pawn_kernel (main stream) + qz_rollout_stuck_kernel (side stream)",
+                "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                "launches_timed": len(roll_ms), "avg_launch_ms": avg_ms, "rollouts_per_launch": avg_n,
-                "share_of_step": sum(roll_ms) / ms if ms > 0 else None,
-                "note": "the rollout keeps the whole game in registers; it is instruction-issue bound, not HBM "
-                        "bound (SURVEY.md 8d), so frac against the HBM peak is tiny by design -- see issue_model and "
-                        "profiles/ for warp-issue efficiency; HBM-bound kernels are listed under `kernels`"}
+                "launches_timed": len(roll_ms), "avg_launch_ms": avg_ms, "avg_main_stream_ms": avg_main,
+                "avg_deferred_stuck_pass_ms": avg_stuck, "rollouts_per_launch": avg_n,
+                "share_of_step": (sum(roll_ms) + sum(stuck_ms)) / ms if ms > 0 else None,
+                "note": "register-resident by design (24 B of state per game): instruction-issue / latency bound, not HBM "
+                        "bound (SURVEY.md 8d), so frac against the HBM peak is ~1e-5 and says nothing; the deferred stuck "
+                        "passes overlap later waves, so share_of_step sums concurrent streams and may exceed 1.  Warp-issue "
+                        "numbers are in profiles/; the HBM-bound kernels (step, encode) are under `kernels` with frac ~1."}
     line = {
         "metric": METRIC, "value": env_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -349,6 +369,11 @@ def run_ours(args):
             line["kernels"] = kernel_section(torch, dev, hbm_peak)
         except Exception as ex:  # the headline must survive a failure of the side section
             line["kernels"] = {"error": repr(ex)}
+    if not args.no_az:
+        try:
+            line["az_mcts"] = az_section(torch, dev, args)
+        except Exception as ex:
+            line["az_mcts"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_pure_mcts_sample(args, args.cpu_seconds)
     else:
@@ -356,6 +381,36 @@ def run_ours(args):
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def az_section(torch, dev, args):
+    """BASELINE configs[2] on this GPU (side measurement, not the headline): AlphaZero MCTS, n_playout = 100,
+    c_puct = 5, random-init 5-block ResNet in bf16, 8192 concurrent games, 4 leaves per game per wave, tree reuse;
+    three self-play plies (search + Dirichlet-mixed move + re-root) timed with CUDA events."""
+    from alphazero_quoridor_b200.policy_value_net import PolicyValueNet
+    from alphazero_quoridor_b200.selfplay import BatchedSelfPlay
+    from alphazero_quoridor_b200.tree import NetEvaluator
+    torch.manual_seed(0)
+    net = PolicyValueNet(use_gpu=True, device=dev)
+    n, npl, K = 8192, 100, 4
+    sp = BatchedSelfPlay(n, NetEvaluator(net), c_puct=5, n_playout=npl, leaves_per_game=K, temp=1.0, pure=False,
+                         seed=args.seed, device=dev)
+    sp.step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(3):
+        sp.step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    out = {"workload": "AlphaZero MCTS n_playout=100, c_puct=5, 5-block ResNet bf16 (random init), 8192 games, K=4, tree reuse",
+           "sims_per_s": 3 * n * npl / ms * 1e3, "ms_per_move": ms / 3, "moves_per_s": 3 * n / ms * 1e3,
+           "net_flops_per_sim": 62.8e6, "net_tflops": 3 * n * npl * 62.8e6 / ms / 1e9,
+           "tree_overflow": sp.mcts.overflow_count()}
+    del sp, net
+    torch.cuda.empty_cache()
+    return out
 
 
 def kernel_section(torch, dev, hbm_peak):
