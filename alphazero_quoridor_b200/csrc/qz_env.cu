@@ -61,11 +61,12 @@ extern "C" int qz_env_step(qz_state *states, const int32_t *actions, const uint6
 // One warp per game (4 games per 128-thread block).
 __global__ void __launch_bounds__(128, 4) qz_legal_mask_kernel(const qz_state *__restrict__ states,
                                                             uint64_t *__restrict__ mask3, int64_t n) {
+    __shared__ uint32_t scratch[4][QZ_WARP_SCRATCH_WORDS];
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n) return;
     const QzState s = qz_load_state(states + g);
     uint32_t pawn; uint64_t hl, vl;
-    qz_warp_legal(s, pawn, hl, vl);
+    qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);
     const int lane = threadIdx.x & 31;
     if (lane < 3) {
         uint64_t out[3];
