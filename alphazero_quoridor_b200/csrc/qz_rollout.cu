@@ -115,13 +115,14 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
 
 // ---- phase 1b: stuck rollouts, one block per rollout ---------------------------------------------------------
 // Every thread tracks the same state redundantly (no broadcasts).  On a ply whose mover owns walls the block
-// runs the full sweep with one flood fill per thread (task = candidate x player), gathers the failures in
-// shared memory, and every thread replays the specified draw sequence against the resulting table
-// (qz_sample_action_known) -- the same action the per-lane path would take, at a latency of ~one flood fill
-// per ply instead of up to 80.
-#define QZ_STUCK_THREADS 128
+// runs the full sweep with one candidate per thread (both players' floods interleaved in that thread:
+// qz_both_reach_goal), gathers the failures in shared memory, and the threads evaluate the specified draw
+// sequence against the resulting table in parallel -- the same action the per-lane path would take, at a latency
+// of ~one flood fill per ply instead of up to 80.  The kernel is latency-bound (one dependent chain per thread),
+// so the block is kept small: more stuck rollouts are resident per SM.
+#define QZ_STUCK_THREADS 64
 
-__global__ void __launch_bounds__(QZ_STUCK_THREADS, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
+__global__ void __launch_bounds__(QZ_STUCK_THREADS, 8) qz_rollout_stuck_kernel(QzRolloutArgs a) {
     __shared__ unsigned long long fail_h, fail_v;
     __shared__ long long sh_entry;
     __shared__ int sh_first[QZ_STUCK_THREADS / 32];
@@ -151,15 +152,10 @@ __global__ void __launch_bounds__(QZ_STUCK_THREADS, 4) qz_rollout_stuck_kernel(Q
                 if (tid == 0) { fail_h = 0; fail_v = 0; }
                 __syncthreads();
                 const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
-                for (int task = tid; task < 2 * total; task += QZ_STUCK_THREADS) {
-                    const int k = task >> 1, player = (task & 1) + 1;
+                for (int k = tid; k < total; k += QZ_STUCK_THREADS) {
                     const bool vert = k >= nh;
                     const int ix = qz_nth_bit64(vert ? vc : hc, vert ? k - nh : k);
-                    QzDirs d = w.dirs;
-                    uint64_t H = s.H, V = s.V;
-                    if (vert) { qz_dirs_place_v(d, ix); V |= 1ull << ix; } else { qz_dirs_place_h(d, ix); H |= 1ull << ix; }
-                    const bool ok = player == 1 ? qz_reaches_goal(d, w.p1, w.p2, 1, H, V) : qz_reaches_goal(d, w.p2, w.p1, 2, H, V);
-                    if (!ok) atomicOr(vert ? &fail_v : &fail_h, 1ull << ix);
+                    if (!qz_wall_keeps_paths(w, ix, vert)) atomicOr(vert ? &fail_v : &fail_h, 1ull << ix);
                 }
                 __syncthreads();
                 hl = hc & ~fail_h;
@@ -272,12 +268,12 @@ extern "C" int64_t qz_rollout_workspace_bytes(int64_t n_rollouts) {
     return 64 + n * (int64_t)sizeof(qz_state) + ((n * 4 + 7) / 8) * 8;
 }
 
-static int qz_persistent_blocks(const void *kernel, int64_t n_items, int items_per_block) {
+static int qz_persistent_blocks(const void *kernel, int64_t n_items, int items_per_block, int threads = 128) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 128, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm <= 0) per_sm = 4;
     int64_t blocks = (int64_t)sms * per_sm;                 // one resident wave: a multiple of the SM count
     const int64_t needed = (n_items + items_per_block - 1) / items_per_block;
     return (int)(blocks < needed ? blocks : needed);
@@ -321,7 +317,7 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
     if (rc) return rc;
     if (!(flags & QZ_ROLLOUT_DEFER_STUCK)) {
         // the number of ejected rollouts is only known on the device: launch a resident grid, blocks exit when the list is empty
-        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1), QZ_STUCK_THREADS, 0, st>>>(a);
+        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1, QZ_STUCK_THREADS), QZ_STUCK_THREADS, 0, st>>>(a);
         rc = qz_check_launch("qz_rollout (stuck phase)");
         if (rc) return rc;
     }
@@ -340,7 +336,7 @@ extern "C" int qz_rollout_finish(const qz_state *states, int64_t n_states, const
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(a.counter + 4, 0, 16, st);
     if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout_finish: memset: %s", cudaGetErrorString(e));
-    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1), QZ_STUCK_THREADS, 0, st>>>(a);
+    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1, QZ_STUCK_THREADS), QZ_STUCK_THREADS, 0, st>>>(a);
     rc = qz_check_launch("qz_rollout_finish (stuck phase)");
     if (rc) return rc;
     a.list_mode = 1;

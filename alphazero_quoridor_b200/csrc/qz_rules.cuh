@@ -413,28 +413,26 @@ QZ_HD_NOINLINE uint32_t qz_jump_set_rebuilt(uint64_t H, uint64_t V, int O, int p
 // Jump edges only ADD reachability, so the search first closes over plain moves alone -- which settles almost
 // every legal candidate -- and builds the jump set (walls H, V = the configuration being tested) only if
 // that closure did not touch the goal row.
-QZ_HD bool qz_reaches_goal(const QzDirs &d, int start, int O, int player, uint64_t H, uint64_t V) {
-    BB reach = bb_bit(start);
+// One closure step of the plain moves (no jumps): reach | moves(reach) & keep.
+QZ_HD BB qz_plain_step(const QzDirs &d, const BB &reach, const BB &keep) {
+    const BB a = bb_shl(bb_and(reach, d.n), 9), b = bb_shr(bb_and(reach, d.s), 9);
+    const BB c = bb_shl(bb_and(reach, d.e), 1), e = bb_shr(bb_and(reach, d.w), 1);
+    BB nxt;
+    nxt.w0 = reach.w0 | ((a.w0 | b.w0 | c.w0 | e.w0) & keep.w0);
+    nxt.w1 = reach.w1 | ((a.w1 | b.w1 | c.w1 | e.w1) & keep.w1);
+    nxt.w2 = reach.w2 | ((a.w2 | b.w2 | c.w2 | e.w2) & keep.w2);
+    return nxt;
+}
+QZ_HD uint32_t qz_goal_hit(const BB &r, int player) { return player == 1 ? (r.w2 & QZ_ROW8_W2) : (r.w0 & QZ_ROW0_W0); }
+
+// Continue a search whose plain-move closure `reach` (a fixpoint that misses the goal row) is known: apply the
+// jump edges, re-close, repeat.  The jump set is built here, lazily (see qz_reaches_goal).
+QZ_HD bool qz_reach_with_jumps(const QzDirs &d, BB reach, int O, int player, uint64_t H, uint64_t V) {
     BB keep = bb_bit(O);
     keep.w0 = ~keep.w0; keep.w1 = ~keep.w1; keep.w2 = ~keep.w2;
-    uint32_t jumps = 0;
-    bool have_jumps = false;
+    const uint32_t jumps = qz_jump_set_rebuilt(H, V, O, player);
+    if (jumps == 0) return false;
     for (;;) {
-        for (;;) {
-            BB a = bb_shl(bb_and(reach, d.n), 9);
-            BB b = bb_shr(bb_and(reach, d.s), 9);
-            BB c = bb_shl(bb_and(reach, d.e), 1);
-            BB e = bb_shr(bb_and(reach, d.w), 1);
-            BB nxt;
-            nxt.w0 = (reach.w0 | ((a.w0 | b.w0 | c.w0 | e.w0) & keep.w0));
-            nxt.w1 = (reach.w1 | ((a.w1 | b.w1 | c.w1 | e.w1) & keep.w1));
-            nxt.w2 = (reach.w2 | ((a.w2 | b.w2 | c.w2 | e.w2) & keep.w2));
-            if (player == 1 ? (nxt.w2 & QZ_ROW8_W2) : (nxt.w0 & QZ_ROW0_W0)) return true;
-            if (bb_eq(nxt, reach)) break;
-            reach = nxt;
-        }
-        if (!have_jumps) { jumps = qz_jump_set_rebuilt(H, V, O, player); have_jumps = true; }
-        if (jumps == 0) return false;
         BB add = bb_zero();
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -448,11 +446,52 @@ QZ_HD bool qz_reaches_goal(const QzDirs &d, int start, int O, int player, uint64
                 if (land >= 0 && land <= 80) add = bb_or(add, bb_bit(land));
             }
         }
-        if (player == 1 ? (add.w2 & QZ_ROW8_W2) : (add.w0 & QZ_ROW0_W0)) return true;
+        if (qz_goal_hit(add, player)) return true;
         BB nxt = bb_or(reach, add);
         if (bb_eq(nxt, reach)) return false;
         reach = nxt;
+        for (;;) {
+            nxt = qz_plain_step(d, reach, keep);
+            if (qz_goal_hit(nxt, player)) return true;
+            if (bb_eq(nxt, reach)) break;
+            reach = nxt;
+        }
     }
+}
+
+QZ_HD bool qz_reaches_goal(const QzDirs &d, int start, int O, int player, uint64_t H, uint64_t V) {
+    BB reach = bb_bit(start);
+    BB keep = bb_bit(O);
+    keep.w0 = ~keep.w0; keep.w1 = ~keep.w1; keep.w2 = ~keep.w2;
+    for (;;) {
+        const BB nxt = qz_plain_step(d, reach, keep);
+        if (qz_goal_hit(nxt, player)) return true;
+        if (bb_eq(nxt, reach)) break;
+        reach = nxt;
+    }
+    return qz_reach_with_jumps(d, reach, O, player, H, V);
+}
+
+// Both searches of _blocks_path (quoridor.py:474-475) advanced in lockstep by one thread: the two closures are
+// independent dependency chains, so interleaving them costs little more time than one.  Returns true iff the wall
+// configuration (d, H, V) leaves both players a path.
+QZ_HD bool qz_both_reach_goal(const QzDirs &d, int p1, int p2, uint64_t H, uint64_t V) {
+    BB r1 = bb_bit(p1), r2 = bb_bit(p2);
+    BB k1 = bb_bit(p2), k2 = bb_bit(p1);
+    k1.w0 = ~k1.w0; k1.w1 = ~k1.w1; k1.w2 = ~k1.w2;
+    k2.w0 = ~k2.w0; k2.w1 = ~k2.w1; k2.w2 = ~k2.w2;
+    bool hit1 = false, hit2 = false, fix1 = false, fix2 = false;
+    while (!((hit1 | fix1) & (hit2 | fix2))) {
+        const BB n1 = qz_plain_step(d, r1, k1), n2 = qz_plain_step(d, r2, k2);     // steps after a verdict are harmless
+        hit1 = hit1 | (qz_goal_hit(n1, 1) != 0);
+        hit2 = hit2 | (qz_goal_hit(n2, 2) != 0);
+        fix1 = bb_eq(n1, r1);
+        fix2 = bb_eq(n2, r2);
+        r1 = n1; r2 = n2;
+    }
+    if (!hit1 && !qz_reach_with_jumps(d, r1, p2, 1, H, V)) return false;
+    if (!hit2 && !qz_reach_with_jumps(d, r2, p1, 2, H, V)) return false;
+    return true;
 }
 
 // ---- wall candidates ------------------------------------------------------------------------------------
@@ -491,8 +530,7 @@ QZ_HD bool qz_wall_keeps_paths(const QzSweep &w, int ix, bool vertical) {
     uint64_t bit = 1ull << ix;
     if (vertical) { qz_dirs_place_v(d, ix); V |= bit; }
     else { qz_dirs_place_h(d, ix); H |= bit; }
-    if (!qz_reaches_goal(d, w.p1, w.p2, 1, H, V)) return false;
-    return qz_reaches_goal(d, w.p2, w.p1, 2, H, V);
+    return qz_both_reach_goal(d, w.p1, w.p2, H, V);
 }
 
 // ---- step (quoridor.py:159-186, :193-202, :217-269) ---------------------------------------------------------
