@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline micro-section")
     ap.add_argument("--no-az", action="store_true", help="skip the AlphaZero-MCTS (BASELINE configs[2]) side measurement")
+    ap.add_argument("--full-games", type=int, default=0, metavar="PLIES",
+                    help="after the timed steps keep playing up to PLIES more plies and report finished self-play games/hr")
     return ap.parse_args()
 
 
@@ -369,6 +371,21 @@ def run_ours(args):
             line["kernels"] = kernel_section(torch, dev, hbm_peak)
         except Exception as ex:  # the headline must survive a failure of the side section
             line["kernels"] = {"error": repr(ex)}
+    if args.full_games > 0:
+        fin0 = sum(int(sub.finished_games.item()) for sub in sp.subs)
+        torch.cuda.synchronize()
+        t_full = time.perf_counter()
+        plies = 0
+        while plies < args.full_games:
+            sp.step()
+            plies += 1
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t_full
+        fin = sum(int(sub.finished_games.item()) for sub in sp.subs) - fin0
+        trunc = sum(int(sub.truncated_games.item()) for sub in sp.subs)
+        line["selfplay_games"] = {"plies_played": plies, "seconds": dt, "games_finished": fin, "games_truncated": trunc,
+                                  "games_per_hr": fin / dt * 3600.0, "note": "pure-MCTS self-play, %d playouts/move, "
+                                  "games restart when they end; measured on rank 0's shard only" % args.playouts}
     if not args.no_az:
         try:
             line["az_mcts"] = az_section(torch, dev, args)
