@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline micro-section")
     ap.add_argument("--no-az", action="store_true", help="skip the AlphaZero-MCTS (BASELINE configs[2]) side measurement")
+    ap.add_argument("--fix-terminal-sign", action="store_true",
+                    help="back up a winning move as a win (the reference backs it up as a loss, mcts.py:125, so its "
+                         "self-play games hardly ever end); default off = reference behaviour")
     ap.add_argument("--full-games", type=int, default=0, metavar="PLIES",
                     help="after the timed steps keep playing up to PLIES more plies and report finished self-play games/hr")
     return ap.parse_args()
@@ -222,7 +225,8 @@ def run_ours(args):
 
     sp = StreamedSelfPlay(args.games, make_evaluator, n_streams=args.streams, c_puct=args.c_puct,
                           n_playout=args.playouts, leaves_per_game=args.leaves, pure=True, seed=args.seed,
-                          game_id_base=rank * args.games, device=dev, defer_depth=args.defer)
+                          game_id_base=rank * args.games, device=dev, defer_depth=args.defer,
+                          fix_terminal_sign=args.fix_terminal_sign)
     engines = [s.mcts for s in sp.subs]
     for m in engines:
         m.count_tree_steps = True
@@ -353,7 +357,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args), "games_per_gpu": args.games, "playouts_per_move": args.playouts,
                    "leaves_per_game_per_wave": args.leaves, "cuda_streams": args.streams,
-                   "stuck_rollout_defer_waves": args.defer,
+                   "stuck_rollout_defer_waves": args.defer, "fix_terminal_sign": bool(args.fix_terminal_sign),
                    "parallelism": "games sharded by index x%d, no collective" % world,
                    "l2": "inputs larger than L2: tree arenas %.1f GB/GPU; rollouts are register resident"
                          % (sum(m.nbytes() for m in engines) / 1e9)},
