@@ -74,9 +74,14 @@ def load():
 LAUNCHES = 0      # kernels of ours launched through the C ABI (bench.py reports it as gpu_launches)
 
 
+# kernels launched by one successful call of each entry point (qz_rollout: wall + stuck + pawn, one fewer when the
+# stuck pass is deferred -- counted as 3 here and 2 for qz_rollout_finish, so a deferred pair is over- by one)
+KERNELS_PER_CALL = {"qz_rollout": 3, "qz_rollout_finish": 2}
+
+
 def check(rc, what=""):
     global LAUNCHES
-    LAUNCHES += 1
+    LAUNCHES += KERNELS_PER_CALL.get(what, 1)
     if rc != 0:
         msg = load().qz_last_error_string().decode("utf-8", "replace")
         raise QzError("%s failed with code %d: %s" % (what or "libqzb200 call", rc, msg))

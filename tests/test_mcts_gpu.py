@@ -304,3 +304,33 @@ def test_deferred_stuck_rollouts(qz):
     tv = 0.5 * np.abs(a[ok] / a[ok].sum(1, keepdims=True) - b[ok] / b[ok].sum(1, keepdims=True)).sum(1)
     print("deferred vs in-wave TV: mean %.4f" % tv.mean())
     assert tv.mean() <= 0.15
+
+
+def test_move_sampling_distributions(qz):
+    """qz_mcts_choose: mode 1 samples the visit-softmax (mcts.py:185), mode 2 samples
+    0.75*probs + 0.25*Dirichlet(0.3) (mcts.py:181) whose mean is 0.75*probs + 0.25/n.  The reference draws from the
+    global numpy RNG, so parity is distributional: 16384 identical trees keyed by different game ids."""
+    n = 16384
+    row = qz.q.pack_state(0, 0, 58, 22, 0, 0, 2)              # pawn-only position with a handful of moves
+    states = torch.tensor([row], dtype=torch.int64).expand(n, 3).contiguous()
+    eng = qz.tree.BatchedMCTS(n, qz.tree.StubEvaluator("S3"), c_puct=5, n_playout=64, leaves_per_game=1, reuse_tree=False)
+    eng.reset(states)
+    eng.search()
+    visits, probs, _ = eng.root_stats(temp=1.0)
+    p = probs[0].cpu().numpy()
+    assert torch.equal(visits, visits[:1].expand_as(visits))             # identical trees
+    legal = np.nonzero(p)[0]
+    nc = len(legal)
+    assert nc >= 3
+    for mode, expect in ((1, p), (2, np.where(p > 0, 0.75 * p + 0.25 / nc, 0.0))):
+        moves = eng.choose(mode=mode, temp=1.0, seed=17).cpu().numpy()
+        assert np.isin(moves, legal).all()
+        counts = np.bincount(moves, minlength=140).astype(np.float64)
+        exp = expect * n
+        chi2 = ((counts[legal] - exp[legal]) ** 2 / exp[legal]).sum()
+        assert chi2 < 40.0, (mode, chi2, counts[legal], exp[legal])      # dof <= 11: far beyond 6 sigma
+        again = eng.choose(mode=mode, temp=1.0, seed=17).cpu().numpy()
+        assert np.array_equal(moves, again)                               # counter-based: reproducible
+    # temp -> 0 concentrates on the most visited move (mcts.py:185 with temp=1e-3)
+    greedy = eng.choose(mode=1, temp=1e-3, seed=3).cpu().numpy()
+    assert (greedy == int(np.argmax(visits[0].cpu().numpy()))).mean() > 0.99

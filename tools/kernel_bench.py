@@ -107,6 +107,28 @@ def main():
             ms = timed(lambda: net.evaluate_states(st))
             out["net_forward_%d" % m] = {"ms": ms, "positions_per_s": m / ms * 1e3,
                                          "TFLOPs": m * 62.8e6 / ms / 1e9}
+    if "cfg4" in which:
+        # BASELINE configs[3], one GPU's shard: 8192 games, n_playout = 800, tree reuse, Dirichlet-mixed moves
+        from alphazero_quoridor_b200.policy_value_net import PolicyValueNet
+        from alphazero_quoridor_b200.selfplay import BatchedSelfPlay
+        from alphazero_quoridor_b200.tree import NetEvaluator
+        torch.manual_seed(0)
+        net = PolicyValueNet(use_gpu=True)
+        sp = BatchedSelfPlay(8192, NetEvaluator(net), c_puct=5, n_playout=800, leaves_per_game=8, temp=1.0, pure=False, seed=1)
+        sp.step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(2):
+            sp.step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        out["cfg4_selfplay_800"] = {"games": 8192, "playouts": 800, "ms_per_move": ms / 2,
+                                    "sims_per_s": 2 * 8192 * 800 / ms * 1e3, "tree_GB": sp.mcts.nbytes() / 1e9,
+                                    "overflow": sp.mcts.overflow_count(),
+                                    "max_nodes_used": int(sp.mcts.arena.n_nodes.max().item()), "node_cap": sp.mcts.node_cap,
+                                    "mem_allocated_GB": torch.cuda.max_memory_allocated() / 1e9}
     print(json.dumps(out, indent=1))
 
 
