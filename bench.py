@@ -347,6 +347,12 @@ def run_ours(args):
                 "launches_timed": len(roll_ms), "avg_launch_ms": avg_ms, "avg_main_stream_ms": avg_main,
                 "avg_deferred_stuck_pass_ms": avg_stuck, "rollouts_per_launch": avg_n,
                 "share_of_step": (sum(roll_ms) + sum(stuck_ms)) / ms if ms > 0 else None,
+                "issue_profile": {"source": "profiles/r1e_rollout_ncu_full.txt, profiles/r1e_sweep_ncu_full.txt (ncu --set full, B200)",
+                                  "smsp_issue_active_pct": {"qz_rollout_wall_kernel": 60.9, "qz_rollout_pawn_kernel": 62.9,
+                                                            "qz_rollout_stuck_kernel": 37.6, "qz_legal_mask_kernel": 63.4},
+                                  "active_lanes_per_instruction": {"qz_rollout_wall_kernel": 18.6, "qz_rollout_pawn_kernel": 17.7,
+                                                                   "qz_rollout_stuck_kernel": 23.3, "qz_legal_mask_kernel": 21.3},
+                                  "note": "static numbers from the committed captures, not measured in this run"},
                 "note": "register-resident by design (24 B of state per game): instruction-issue / latency bound, not HBM "
                         "bound (SURVEY.md 8d), so frac against the HBM peak is ~1e-5 and says nothing; the deferred stuck "
                         "passes overlap later waves, so share_of_step sums concurrent streams and may exceed 1.  Warp-issue "
