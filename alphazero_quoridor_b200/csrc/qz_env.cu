@@ -86,6 +86,45 @@ extern "C" int qz_env_legal_mask(const qz_state *states, uint64_t *mask3, int64_
     return qz_check_launch("qz_env_legal_mask");
 }
 
+// ------------------------------------------------------------------------------------------ uniform legal pick
+// The reference's random policy (pure_mcts.py:7-10: argmax of iid U(0,1) over actions() == a uniform legal action)
+// given the FULL legal mask: action = k-th set bit of the mask, k = (word * count) >> 32, word = Philox4x32-10(key =
+// seed; counter = (game id, ply >> 2, 0x7000))[ply & 3] with ply read from the state.  One game per thread.
+// Finished games and games without a legal action get -1.
+#include "qz_philox.cuh"
+
+__global__ void qz_sample_legal_kernel(const qz_state *__restrict__ states, const uint64_t *__restrict__ mask3, uint64_t seed,
+                                       const int64_t *__restrict__ game_id, int32_t *__restrict__ actions, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t meta = __ldg(reinterpret_cast<const uint64_t *>(states + i) + 2);
+    const uint64_t m0 = __ldg(mask3 + 3 * i), m1 = __ldg(mask3 + 3 * i + 1), m2 = __ldg(mask3 + 3 * i + 2);
+    const int c0 = qz_popc64(m0), c1 = qz_popc64(m1), cnt = c0 + c1 + qz_popc64(m2);
+    int act = -1;
+    if (!qz_done(meta) && cnt > 0) {
+        const uint32_t ply = qz_ply(meta);
+        const QzPhilox4 b = qz_philox(seed, game_id ? (uint64_t)game_id[i] : (uint64_t)i, ply >> 2, 0x7000u);
+        int k = (int)qz_mulhi32(qz_philox_word(b, (int)(ply & 3u)), (uint32_t)cnt);
+        if (k < c0) act = qz_nth_bit64(m0, k);
+        else if (k < c0 + c1) act = 64 + qz_nth_bit64(m1, k - c0);
+        else act = 128 + qz_nth_bit64(m2, k - c0 - c1);
+    }
+    actions[i] = act;
+}
+
+extern "C" int qz_env_sample_legal(const qz_state *states, const uint64_t *mask3, uint64_t seed, const int64_t *game_id,
+                                   int32_t *actions, int64_t n, void *stream) {
+    QZ_REQUIRE(n >= 0);
+    if (n == 0) return 0;
+    QZ_REQUIRE_PTR(states);
+    QZ_REQUIRE_PTR(mask3);
+    QZ_REQUIRE_PTR(actions);
+    QZ_REQUIRE_ALIGN(states, 8);
+    QZ_REQUIRE_ALIGN(mask3, 8);
+    qz_sample_legal_kernel<<<qz_blocks_for(n, 256), 256, 0, (cudaStream_t)stream>>>(states, mask3, seed, game_id, actions, n);
+    return qz_check_launch("qz_env_sample_legal");
+}
+
 // ------------------------------------------------------------------------------------------ encode
 // HBM-bound by design: 24 B read and 2106 (NCHW) / 81*c_stride (NHWC) elements written per game.
 // A block of 8 warps encodes 8 games.  Phase 1 builds the block's output as a packed BIT stream in shared

@@ -114,6 +114,31 @@ class BatchedQuoridor:
                                             _lib.ptr(done), self.n, self._stream()), "qz_env_step")
         return done
 
+    def sample_actions(self, legal_mask, seed=0, game_id=None, out=None):
+        """One uniformly random legal action per game from its full legal mask (pure_mcts.py:7-10), int32 [n];
+        -1 for finished / stalemated games.  Philox stream keyed by (seed, game_id[i] or i, ply)."""
+        if out is None:
+            out = torch.empty((self.n,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qz_env_sample_legal(_lib.ptr(self.states), _lib.ptr(legal_mask), int(seed) & M64,
+                                                    _lib.ptr(game_id), _lib.ptr(out), self.n, self._stream()),
+                       "qz_env_sample_legal")
+        return out
+
+    def random_play(self, seed=0, max_plies=3000, game_id=None, check_every=16):
+        """BASELINE config 1: uniform-random legal play to terminal with the FULL legal mask computed every ply
+        (legal_mask -> sample_actions -> step).  Returns the number of plies played per game (int64 [n])."""
+        mask = torch.empty((self.n, 3), dtype=torch.int64, device=self.device)
+        acts = torch.empty((self.n,), dtype=torch.int32, device=self.device)
+        done = torch.empty((self.n,), dtype=torch.uint8, device=self.device)
+        for ply in range(max_plies):
+            self.legal_mask(out=mask)
+            self.sample_actions(mask, seed=seed, game_id=game_id, out=acts)
+            self.step(acts, done=done)
+            if ply % check_every == check_every - 1 and bool(((done != 0) | (acts < 0)).all()):
+                break
+        return (self.states[:, 2] >> 48) & 0xFFFF
+
     def encode(self, out=None, dtype=torch.float32, channels_last=False, c_stride=26):
         """Quoridor.state for every game (quoridor.py:58-131), written as `dtype` into `out`.
         NCHW: out [n,26,9,9] contiguous.  channels_last: out is a [n,c_stride,9,9] tensor in

@@ -479,6 +479,22 @@ def kernel_section(torch, dev, hbm_peak):
         out["qz_encode_kernel_" + name] = {"units": n2, "ms": ms, "bytes_per_unit": nb // n2,
                                            "achieved_GBps": nb / ms / 1e6, "frac_hbm": nb / ms / 1e6 / hbm_peak, "bound": "hbm"}
         del buf
+    # BASELINE config 1 literally: random games with the FULL legal mask computed every ply (3 launches per ply)
+    ng = 1 << 18
+    envg = BatchedQuoridor(ng, device=dev)
+    envg.random_play(seed=1, max_plies=48)
+    envg.reset()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    plies = envg.random_play(seed=2, max_plies=3000)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b)
+    out["random_play_full_mask"] = {"games": ng, "ms": ms, "env_steps_per_s": float(plies.sum().item()) / ms * 1e3,
+                                    "mean_plies": float(plies.float().mean().item()),
+                                    "workload": "BASELINE config 1: reset() to terminal, legal_mask + sample_legal + step per ply"}
+    del envg
     n3 = 1 << 24     # 403 MB of states: larger than L2
     env3 = BatchedQuoridor(n3, device=dev)
     acts = torch.full((n3,), 2, dtype=torch.int32, device=dev)       # E then (opponent) E ... never terminal

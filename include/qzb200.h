@@ -99,6 +99,16 @@ int qz_env_step(qz_state *states, const int32_t *actions, const uint64_t *legal_
 int qz_env_legal_mask(const qz_state *states, uint64_t *mask3, int64_t n, void *stream);
 
 /*
+ * The reference's random policy over the FULL legal set (pure_mcts.rollout_policy_fn, pure_mcts.py:7-10: argmax of
+ * iid uniforms over actions() == one uniform legal action): actions[i] = the k-th set bit of game i's legal mask,
+ * k = (word * popcount) >> 32, word = Philox4x32-10(key = seed, counter = (game_id[i] or i, ply >> 2, 0x7000))[ply & 3].
+ * -1 for finished games and games with an empty mask.  With qz_env_legal_mask and qz_env_step this is BASELINE
+ * config 1 literally: "env step + valid-action mask" for every ply of a random game.
+ */
+int qz_env_sample_legal(const qz_state *states, const uint64_t *mask3, uint64_t seed, const int64_t *game_id,
+                        int32_t *actions, int64_t n, void *stream);
+
+/*
  * Quoridor.state (quoridor.py:58-131): the 26 x 9 x 9 planes of each game, written in `dtype`
  * straight into the policy-value net's input buffer.
  *   layout NCHW: out is [n][26][9][9].   layout NHWC: out is [n][9][9][c_stride], channels >= 26 zeroed.

@@ -79,6 +79,8 @@ def lib():
         L.oq_bench_stub_mcts.restype = C.c_longlong
         L.oq_max_threads.restype = C.c_int
         L.oq_set_literal_rollouts.argtypes = [C.c_int]
+        L.oq_random_game.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int]
+        L.oq_random_game.restype = C.c_int
         _lib = L
     return _lib
 
@@ -140,6 +142,10 @@ class OracleGame:
         if rc != 0:
             raise IndexError("reference undefined: pawn off the board")
         return out
+
+    def random_game(self, seed, game_id, cap=3000):
+        """Play self to the end with uniform picks from the full legal list (product's pick rule). -> plies."""
+        return self._L.oq_random_game(self._g, seed, game_id, cap)
 
     def state_key(self):
         return self._L.oq_state_key(self._g)

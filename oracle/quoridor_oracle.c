@@ -680,6 +680,30 @@ void oq_mcts_update_with_move(oq_mcts *t, int last_move) {
     t->root = node_new(NULL, 1.0);
 }
 
+/* Uniform-random legal play with the FULL legal list every ply (BASELINE config 1) and the product's pick rule
+ * (qz_env_sample_legal): the legal actions sorted by action id, k = (word * n) >> 32,
+ * word = Philox(ctr = (game id, ply >> 2, 0x7000))[ply & 3].  Plays g to the end (or cap plies); returns plies played. */
+int oq_random_game(oq_game *g, uint64_t seed, uint64_t game_id, int cap) {
+    int plies = 0;
+    while (plies < cap) {
+        int winner;
+        if (oq_has_a_winner(g, &winner)) break;
+        int acts[140], present[140];
+        int n = oq_actions(g, acts);
+        if (n == 0) break;
+        memset(present, 0, sizeof(present));
+        for (int i = 0; i < n; i++) present[acts[i]] = 1;
+        uint32_t w[4];
+        oq_philox(seed, game_id, (uint32_t)plies >> 2, 0x7000u, w);
+        int k = (int)(((uint64_t)w[plies & 3] * (uint32_t)n) >> 32);
+        int a = -1;
+        for (int id = 0; id < 140; id++) if (present[id] && k-- == 0) { a = id; break; }
+        oq_step(g, a);
+        plies++;
+    }
+    return plies;
+}
+
 /* ---------------------------------------------------------------- CPU-baseline drivers (bench.py)
  * A minimal pthread parallel-for with dynamic (atomic counter) scheduling: one work item per game /
  * position, all host threads the caller asks for. */

@@ -281,3 +281,24 @@ def test_stuck_rollouts_vs_oracle(qz):
             pos_o["H"], pos_o["V"], pos_o["p1"], pos_o["p2"], pos_o["w1"], pos_o["w2"], pos_o["cur"])
         n_long += (f["w1"] + f["w2"]) > 0          # still holding walls at the end: stuck all the way
     assert n_long >= 10
+
+
+def test_full_mask_random_games_vs_oracle(qz):
+    """BASELINE config 1, literally: every ply = full legal mask + uniform pick + step.  384 whole games played by
+    the three kernels == the oracle's games (literal actions()/step with the same Philox picks): length, winner
+    and final position."""
+    n, seed = 384, 31337
+    env = qz.BatchedQuoridor(n)
+    gid = torch.arange(1000, 1000 + n, dtype=torch.int64, device=env.device)
+    plies = env.random_play(seed=seed, max_plies=3000, game_id=gid).cpu().numpy()
+    hs = env.host_states()
+    for i in range(0, n, 2):
+        g = O.OracleGame()
+        k = g.random_game(seed, 1000 + i, 3000)
+        pos = g.position()
+        d = hs[i]
+        assert k == plies[i], i
+        assert (d["H"], d["V"], d["p1"], d["p2"], d["w1"], d["w2"], d["cur"]) == (
+            pos["H"], pos["V"], pos["p1"], pos["p2"], pos["w1"], pos["w2"], pos["cur"])
+        assert d["done"] == g.has_a_winner()[0] and d["winner"] == (g.has_a_winner()[1] or 0)
+    assert 200 < plies.mean() < 500 and np.mean([d["done"] for d in hs]) > 0.97      # a few games hit the ply cap
