@@ -113,29 +113,24 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
     }
 }
 
-// ---- phase 1b: stuck rollouts, one block per rollout ---------------------------------------------------------
-// Every thread tracks the same state redundantly (no broadcasts).  On a ply whose mover owns walls the block
-// runs the full sweep with one candidate per thread (both players' floods interleaved in that thread:
-// qz_both_reach_goal), gathers the failures in shared memory, and the threads evaluate the specified draw
-// sequence against the resulting table in parallel -- the same action the per-lane path would take, at a latency
-// of ~one flood fill per ply instead of up to 80.  The kernel is latency-bound (one dependent chain per thread),
-// so the block is kept small: more stuck rollouts are resident per SM.
-#define QZ_STUCK_THREADS 64
+// ---- phase 1b: stuck rollouts, one WARP per rollout -----------------------------------------------------------
+// Every lane tracks the same state redundantly (no broadcasts).  The draw sequence of qz_sample.cuh is made of
+// independent attempts, so the warp evaluates 32 of them at once: lane i decodes attempt 32*round + i.  A pawn
+// move is legal as it stands, hence only the wall attempts BEFORE the first pawn attempt of the round can matter;
+// exactly those are path-checked (one candidate per lane, both players' floods interleaved in that lane) and the
+// earliest legal attempt wins -- the same action the per-lane path would take.  In a stuck position ~4 % of the
+// attempts are pawn moves, so a ply costs about one flood-fill latency and ~25 path checks instead of the ~70 of
+// a full sweep, and a rollout occupies one warp: the pass is latency-bound, so its throughput is the number of
+// rollouts resident per SM.
 
-__global__ void __launch_bounds__(QZ_STUCK_THREADS, 8) qz_rollout_stuck_kernel(QzRolloutArgs a) {
-    __shared__ unsigned long long fail_h, fail_v;
-    __shared__ long long sh_entry;
-    __shared__ int sh_first[QZ_STUCK_THREADS / 32];
-    const int tid = threadIdx.x;
+__global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
+    const int lane = threadIdx.x & 31;
     for (;;) {
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned long long k = atomicAdd(a.counter + 4, 1ull);
-            sh_entry = k < a.counter[3] ? (long long)a.stuck_list[k] : -1;
-        }
-        __syncthreads();
-        const int64_t r = sh_entry;
-        if (r < 0) break;
+        unsigned long long k = 0;
+        if (lane == 0) k = atomicAdd(a.counter + 4, 1ull);
+        k = __shfl_sync(QZ_FULL_MASK, k, 0);
+        if (k >= a.counter[3]) break;
+        const int64_t r = a.stuck_list[k];
         QzState s = qz_load_state(a.mid + r);
         s.meta &= ~((uint64_t)QZ_FLAG_PENDING << 40);
         const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, r)) + 2);
@@ -145,47 +140,44 @@ __global__ void __launch_bounds__(QZ_STUCK_THREADS, 8) qz_rollout_stuck_kernel(Q
             if (qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0) break;
             const QzPawnCtx c = qz_ctx_build(s.H, s.V);
             const uint32_t pawn = qz_mover_pawn_moves_ctx(c, s.meta);
-            uint64_t hl = 0, vl = 0, hc = 0, vc = 0;
-            if (qz_mover_walls(s.meta) > 0) {
-                hc = qz_hcand(s.H, s.V); vc = qz_vcand(s.H, s.V);
-                const int nh = qz_popc64(hc), total = nh + qz_popc64(vc);
-                if (tid == 0) { fail_h = 0; fail_v = 0; }
-                __syncthreads();
-                const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
-                for (int k = tid; k < total; k += QZ_STUCK_THREADS) {
-                    const bool vert = k >= nh;
-                    const int ix = qz_nth_bit64(vert ? vc : hc, vert ? k - nh : k);
-                    if (!qz_wall_keeps_paths(w, ix, vert)) atomicOr(vert ? &fail_v : &fail_h, 1ull << ix);
-                }
-                __syncthreads();
-                hl = hc & ~fail_h;
-                vl = vc & ~fail_v;
-                __syncthreads();                    // everyone has read the table before the next ply clears it
-            }
-            // the attempts of qz_sample.cuh are independent draws: thread i evaluates attempt round*128 + i against
-            // the table and the first legal one wins -- the action qz_sample_action_known would return
-            const int npawn = qz_popc32(pawn), nh2 = qz_popc64(hc);
-            const uint32_t M = (uint32_t)(npawn + nh2 + qz_popc64(vc));
+            const bool has_walls = qz_mover_walls(s.meta) > 0;
+            const uint64_t hc = has_walls ? qz_hcand(s.H, s.V) : 0ull, vc = has_walls ? qz_vcand(s.H, s.V) : 0ull;
+            const int npawn = qz_popc32(pawn), nh = qz_popc64(hc), nv = qz_popc64(vc);
+            const uint32_t M = (uint32_t)(npawn + nh + nv);
             int act = -1;
-            if (M != 0 && !(npawn == 0 && (hl | vl) == 0)) {
+            if (M != 0 && !has_walls) {                                  // only pawn moves: attempt 0 is legal
+                act = qz_nth_bit64((uint64_t)pawn, (int)qz_mulhi32(qz_attempt_word(rng, (uint32_t)steps, 0), M));
+            } else if (M != 0) {
+                const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
+                uint64_t bad_h = 0, bad_v = 0;                          // walls already known to block (warp-uniform)
                 for (uint32_t round = 0; act < 0; round++) {
-                    const uint32_t word = qz_attempt_word(rng, (uint32_t)steps, round * QZ_STUCK_THREADS + tid);
-                    const int cand = qz_superset_action(pawn, hc, vc, npawn, nh2, (int)qz_mulhi32(word, M));
-                    const bool legal = cand < 12 || (cand < 76 ? (hl >> (cand - 12)) & 1ull : (vl >> (cand - 76)) & 1ull);
-                    const unsigned bal = __ballot_sync(QZ_FULL_MASK, legal);
-                    const int first = bal ? __shfl_sync(QZ_FULL_MASK, cand, __ffs(bal) - 1) : -1;
-                    if ((tid & 31) == 0) sh_first[tid >> 5] = first;
-                    __syncthreads();
-#pragma unroll
-                    for (int wq = QZ_STUCK_THREADS / 32 - 1; wq >= 0; wq--) if (sh_first[wq] >= 0) act = sh_first[wq];
-                    __syncthreads();
+                    const uint32_t word = qz_attempt_word(rng, (uint32_t)steps, round * 32 + lane);
+                    const int cand = qz_superset_action(pawn, hc, vc, npawn, nh, (int)qz_mulhi32(word, M));
+                    const unsigned pawn_lanes = __ballot_sync(QZ_FULL_MASK, cand < 12);
+                    const int first_pawn = pawn_lanes ? __ffs(pawn_lanes) - 1 : 32;
+                    bool ok = false;
+                    if (lane < first_pawn) {                             // a wall attempt that can still win the draw
+                        const bool vert = cand >= 76;
+                        const int ix = vert ? cand - 76 : cand - 12;
+                        if (!(((vert ? bad_v : bad_h) >> ix) & 1ull)) ok = qz_wall_keeps_paths(w, ix, vert);
+                    }
+                    const unsigned ok_lanes = __ballot_sync(QZ_FULL_MASK, ok);
+                    const int winner = ok_lanes ? __ffs(ok_lanes) - 1 : first_pawn;      // earliest legal attempt
+                    if (winner < 32) { act = __shfl_sync(QZ_FULL_MASK, cand, winner); break; }
+                    // all 32 attempts were blocking walls: remember them; with no pawn move at all, stop once every
+                    // candidate is known to block (stalemate; the reference would return [] and crash)
+                    const bool vert = cand >= 76;
+                    const int ix = vert ? cand - 76 : cand - 12;
+                    bad_h |= qz_warp_or64(vert ? 0ull : 1ull << ix);
+                    bad_v |= qz_warp_or64(vert ? 1ull << ix : 0ull);
+                    if (npawn == 0 && bad_h == hc && bad_v == vc) break;
                 }
             }
             if (act < 0) { s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40; break; }
             s = qz_apply(s, act);
             steps++;
         }
-        if (tid == 0) qz_store_state(a.mid + r, s);
+        if (lane == 0) qz_store_state(a.mid + r, s);
     }
 }
 
@@ -317,7 +309,7 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
     if (rc) return rc;
     if (!(flags & QZ_ROLLOUT_DEFER_STUCK)) {
         // the number of ejected rollouts is only known on the device: launch a resident grid, blocks exit when the list is empty
-        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1, QZ_STUCK_THREADS), QZ_STUCK_THREADS, 0, st>>>(a);
+        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 4, 128), 128, 0, st>>>(a);
         rc = qz_check_launch("qz_rollout (stuck phase)");
         if (rc) return rc;
     }
@@ -336,7 +328,7 @@ extern "C" int qz_rollout_finish(const qz_state *states, int64_t n_states, const
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(a.counter + 4, 0, 16, st);
     if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout_finish: memset: %s", cudaGetErrorString(e));
-    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 1, QZ_STUCK_THREADS), QZ_STUCK_THREADS, 0, st>>>(a);
+    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 4, 128), 128, 0, st>>>(a);
     rc = qz_check_launch("qz_rollout_finish (stuck phase)");
     if (rc) return rc;
     a.list_mode = 1;
