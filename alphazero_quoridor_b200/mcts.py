@@ -84,6 +84,65 @@ def _make_evaluator(policy_value_fn):
     return _CallbackEvaluator(policy_value_fn)
 
 
+class TreeNode(object):
+    """Read-only view of one node of the device tree with the reference's TreeNode surface (mcts.py:12-80):
+    `_n_visits`, `_Q`, `_P`, `_u`, `_children` (dict action -> TreeNode, in insertion order), `_parent`,
+    `is_leaf()`, `is_root()`, `get_value(c_puct)`.  The statistics live in the flat device arrays of
+    tree.BatchedMCTS; this object copies what it is asked for.  Mutation (expand/update/select) happens in the
+    kernels, so those methods are not offered here."""
+
+    def __init__(self, engine, game_index, node, parent=None, uniform_prior=False):
+        self._engine, self._g, self._node, self._parent = engine, game_index, int(node), parent
+        self._uniform = uniform_prior
+
+    def _at(self, name):
+        a = self._engine.arena
+        return getattr(a, name)[self._g * self._engine.node_cap + self._node].item()
+
+    @property
+    def _n_visits(self):
+        return int(self._at("visits"))
+
+    @property
+    def _Q(self):
+        return float(self._at("q"))
+
+    @property
+    def _P(self):
+        if self._uniform and self._parent is not None:
+            return 1.0 / len(self._parent._children)
+        return float(np.float32(self._at("prior")))
+
+    @property
+    def _children(self):
+        eng = self._engine
+        base = int(self._at("child_base"))
+        if base < 0:
+            return {}
+        o = self._g * eng.node_cap
+        nc = (int(self._at("node_meta")) >> 8) & 0xFF
+        acts = eng.arena.node_meta[o + base:o + base + nc].cpu().numpy()
+        return {int(a) & 0xFF: TreeNode(eng, self._g, base + j, self, self._uniform) for j, a in enumerate(acts)}
+
+    @property
+    def _u(self):
+        return self.get_value(self._engine.c_puct) - self._Q if self._parent is not None else 0
+
+    def get_value(self, c_puct):
+        """mcts.py:64-70 with numpy's promotion (float32 prior * weak scalar rounds to float32 first)."""
+        if self._uniform:
+            cp = c_puct * self._P
+        else:
+            cp = float(np.float32(c_puct) * np.float32(self._at("prior")))
+        return self._Q + cp * np.sqrt(self._parent._n_visits) / (1 + self._n_visits)
+
+    def is_leaf(self):
+        return int(self._at("child_base")) < 0
+
+    def is_root(self):
+        return self._parent is None
+
+
 class MCTS(object):
     """mcts.py:83-154"""
 
@@ -101,6 +160,18 @@ class MCTS(object):
     def _set_root_state(self, game):
         row = torch.tensor([game.packed()], dtype=torch.int64, device=self._engine.device)
         self._engine.root_state.copy_(row)
+
+    @property
+    def _root(self):
+        """The root as a reference-style TreeNode view (mcts.py:97)."""
+        self._engine.drain()
+        return TreeNode(self._engine, 0, int(self._engine.arena.root[0].item()))
+
+    def _playout(self, game):
+        """mcts.py:103-127: ONE playout from `game` (the reference mutates the game copy it is given; here the
+        descent replays the moves on the device and `game` is left untouched)."""
+        self._set_root_state(game)
+        self._engine.playout_wave(1)
 
     def get_move_probs(self, game, temp=1e-3):
         """mcts.py:129-144: n_playout playouts from `game`, then (acts, probs) over the root's children in

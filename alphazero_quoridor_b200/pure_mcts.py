@@ -8,7 +8,13 @@ import numpy as np
 import torch
 
 from . import tree as _tree
+from .mcts import TreeNode as _TreeNodeView
 from .quoridor import Quoridor
+from .rollout import rollout as _rollout
+
+
+class TreeNode(_TreeNodeView):
+    """pure_mcts.py:19-56 -- read-only view, priors are the uniform 1/len(children) of pure_mcts.py:13-16."""
 
 
 def rollout_policy_fn(game):
@@ -38,6 +44,26 @@ class MCTS(object):
                                          leaves_per_game=leaves_per_game, fix_terminal_sign=fix_terminal_sign,
                                          reuse_tree=False, device=device)
         self._engine.reset(torch.tensor([Quoridor().packed()], dtype=torch.int64))
+
+    @property
+    def _root(self):
+        self._engine.drain()
+        return TreeNode(self._engine, 0, int(self._engine.arena.root[0].item()), None, True)
+
+    def _playout(self, game):
+        """pure_mcts.py:66-83: one playout (descent, expansion, random rollout, backup) from `game`."""
+        row = torch.tensor([game.packed()], dtype=torch.int64, device=self._engine.device)
+        self._engine.root_state.copy_(row)
+        self._engine.playout_wave(1)
+
+    def _evaluate_rollout(self, game, limit=1000):
+        """pure_mcts.py:86-108: one uniformly random playout of at most limit-1 plies from `game`; +1 / -1 from
+        the point of view of the side to move in `game`, 0 if nobody won.  (`game` itself is not advanced.)"""
+        row = torch.tensor([game.packed()], dtype=torch.int64, device=self._engine.device)
+        self._rollouts_done = getattr(self, "_rollouts_done", 0) + 1
+        res, _, _ = _rollout(row, per_state=1, seed=self._evaluator.seed, rid_base=(1 << 40) + self._rollouts_done,
+                             limit=limit, return_plies=False)
+        return int(res.item())
 
     def get_move(self, game):
         """pure_mcts.py:110-115"""

@@ -334,3 +334,32 @@ def test_move_sampling_distributions(qz):
     # temp -> 0 concentrates on the most visited move (mcts.py:185 with temp=1e-3)
     greedy = eng.choose(mode=1, temp=1e-3, seed=3).cpu().numpy()
     assert (greedy == int(np.argmax(visits[0].cpu().numpy()))).mean() > 0.99
+
+
+def test_reference_private_surface(qz, mcts_golden):
+    """`MCTS._root` (TreeNode view: _children/_n_visits/_Q/_P/is_leaf/get_value), `_playout`, and
+    pure `_evaluate_rollout` -- the members tests and tools of the reference reach into (mcts.py:12-127)."""
+    case = [c for c in mcts_golden if c["name"] == "late_b_S2_800"][0]
+    t = qz.mcts.MCTS(qz.mcts.DeviceStub("S2"), case["c_puct"], case["n_playout"])
+    g = _facade(qz, case["moves"][0]["pos"])
+    assert t._root.is_leaf() and t._root.is_root() and t._root._n_visits == 0
+    t._playout(g)
+    assert not t._root.is_leaf() and t._root._n_visits == 1
+    t2 = qz.mcts.MCTS(qz.mcts.DeviceStub("S2"), case["c_puct"], case["n_playout"])
+    t2.get_move_probs(g, 1.0)
+    root = t2._root
+    kids = root._children
+    mv = case["moves"][0]
+    assert list(kids.keys()) == mv["acts"]
+    assert [k._n_visits for k in kids.values()] == mv["visits"]
+    assert [k._Q for k in kids.values()] == mv["q"]
+    assert root._n_visits == mv["root_visits"] and root._Q == mv["root_q"]
+    best = max(kids.items(), key=lambda kv: kv[1].get_value(case["c_puct"]))      # TreeNode.select, mcts.py:42
+    assert best[0] in mv["acts"] and all(0 < k._P <= 2 ** -6 for k in kids.values())
+    # pure MCTS
+    p = qz.pure.MCTS(c_puct=5, n_playout=20, seed=4)
+    h = qz.q.Quoridor()
+    vals = [p._evaluate_rollout(h) for _ in range(8)]
+    assert set(vals) <= {-1, 0, 1} and h._positions == {1: 4, 2: 76}
+    p._playout(h)
+    assert abs(p._root._children[0]._P - 1.0 / 131) < 1e-15 and p._root._n_visits == 1
