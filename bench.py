@@ -37,7 +37,7 @@ def parse():
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
     ap.add_argument("--playouts", type=int, default=1000)
     ap.add_argument("--leaves", type=int, default=64, help="leaves per game per wave (virtual loss)")
-    ap.add_argument("--streams", type=int, default=1, help="sub-batches of games on separate CUDA streams")
+    ap.add_argument("--streams", type=int, default=2, help="sub-batches of games on separate CUDA streams")
     ap.add_argument("--defer", type=int, default=4, help="waves a stuck rollout may lag behind (0 = finish in-wave)")
     ap.add_argument("--c-puct", type=float, default=5.0)
     ap.add_argument("--seed", type=int, default=20261017)
