@@ -35,6 +35,7 @@ SIGNATURES = {
     "qz_env_legal_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
     "qz_env_encode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _i64, _vp]),
     "qz_env_sample_legal": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _i64, _vp]),
+    "qz_env_random_play": (C.c_int, [_vp, _u64, _vp, _i32, _i64, _vp]),
     "qz_rollout_workspace_bytes": (C.c_int64, [_i64]),
     "qz_rollout": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "qz_rollout_finish": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
@@ -77,7 +78,7 @@ LAUNCHES = 0      # kernels of ours launched through the C ABI (bench.py reports
 
 # kernels launched by one successful call of each entry point (qz_rollout: wall + stuck + pawn, one fewer when the
 # stuck pass is deferred -- counted as 3 here and 2 for qz_rollout_finish, so a deferred pair is over- by one)
-KERNELS_PER_CALL = {"qz_rollout": 3, "qz_rollout_finish": 2}
+KERNELS_PER_CALL = {"qz_rollout": 3, "qz_rollout_finish": 2, "qz_env_random_play": 2}
 
 
 def check(rc, what=""):

@@ -125,6 +125,72 @@ extern "C" int qz_env_sample_legal(const qz_state *states, const uint64_t *mask3
     return qz_check_launch("qz_env_sample_legal");
 }
 
+// ------------------------------------------------------------------------------------------ whole random games
+// BASELINE config 1 in two launches: uniform-random legal play with the FULL legal set computed on every ply and the
+// pick rule of qz_env_sample_legal, played to the end (or max_plies) inside the kernels -- the same games, ply for ply,
+// as the legal_mask / sample_legal / step loop.  While a wall is still in hand a game is driven by one warp (the
+// 128-candidate sweep of qz_warp_legal per ply); afterwards by one thread (twelve corner masks built once, a pawn-move
+// query per ply).
+__device__ __forceinline__ int qz_pick_from_mask(uint32_t pawn, uint64_t hl, uint64_t vl, uint64_t seed, uint64_t gid, uint32_t ply) {
+    uint64_t m[3];
+    qz_pack_mask(pawn, hl, vl, m);
+    const int c0 = qz_popc64(m[0]), c1 = qz_popc64(m[1]), cnt = c0 + c1 + qz_popc64(m[2]);
+    if (cnt == 0) return -1;
+    const QzPhilox4 b = qz_philox(seed, gid, ply >> 2, 0x7000u);
+    const int k = (int)qz_mulhi32(qz_philox_word(b, (int)(ply & 3u)), (uint32_t)cnt);
+    if (k < c0) return qz_nth_bit64(m[0], k);
+    if (k < c0 + c1) return 64 + qz_nth_bit64(m[1], k - c0);
+    return 128 + qz_nth_bit64(m[2], k - c0 - c1);
+}
+
+__global__ void __launch_bounds__(128, 4) qz_random_play_wall_kernel(qz_state *__restrict__ states, uint64_t seed,
+                                                                     const int64_t *__restrict__ game_id, int max_plies, int64_t n) {
+    __shared__ uint32_t scratch[4][QZ_WARP_SCRATCH_WORDS];
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    QzState s = qz_load_state(states + g);
+    const uint64_t gid = game_id ? (uint64_t)game_id[g] : (uint64_t)g;
+    while (!qz_done(s.meta) && !(qz_flags(s.meta) & QZ_FLAG_STALEMATE) && (int)qz_ply(s.meta) < max_plies &&
+           qz_w1(s.meta) + qz_w2(s.meta) > 0) {
+        uint32_t pawn; uint64_t hl, vl;
+        qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);
+        const int act = qz_pick_from_mask(pawn, hl, vl, seed, gid, qz_ply(s.meta));
+        if (act < 0) s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40;
+        else s = qz_apply(s, act);
+    }
+    if ((threadIdx.x & 31) == 0) qz_store_state(states + g, s);
+}
+
+__global__ void __launch_bounds__(128) qz_random_play_pawn_kernel(qz_state *__restrict__ states, uint64_t seed,
+                                                                  const int64_t *__restrict__ game_id, int max_plies, int64_t n) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    QzState s = qz_load_state(states + g);
+    if (qz_done(s.meta) || (qz_flags(s.meta) & QZ_FLAG_STALEMATE) || qz_w1(s.meta) + qz_w2(s.meta) > 0) return;
+    const uint64_t gid = game_id ? (uint64_t)game_id[g] : (uint64_t)g;
+    const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+    while (!qz_done(s.meta) && (int)qz_ply(s.meta) < max_plies) {
+        const int act = qz_pick_from_mask(qz_mover_pawn_moves_ctx(c, s.meta), 0, 0, seed, gid, qz_ply(s.meta));
+        if (act < 0) { s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40; break; }
+        s = qz_apply(s, act);
+    }
+    qz_store_state(states + g, s);
+}
+
+extern "C" int qz_env_random_play(qz_state *states, uint64_t seed, const int64_t *game_id, int32_t max_plies, int64_t n,
+                                  void *stream) {
+    QZ_REQUIRE(n >= 0 && max_plies >= 0 && max_plies <= 65535);
+    if (n == 0) return 0;
+    QZ_REQUIRE_PTR(states);
+    QZ_REQUIRE_ALIGN(states, 8);
+    cudaStream_t st = (cudaStream_t)stream;
+    qz_random_play_wall_kernel<<<qz_blocks_for(n, 4), 128, 0, st>>>(states, seed, game_id, max_plies, n);
+    int rc = qz_check_launch("qz_env_random_play (wall phase)");
+    if (rc) return rc;
+    qz_random_play_pawn_kernel<<<qz_blocks_for(n, 128), 128, 0, st>>>(states, seed, game_id, max_plies, n);
+    return qz_check_launch("qz_env_random_play (pawn phase)");
+}
+
 // ------------------------------------------------------------------------------------------ encode
 // HBM-bound by design: 24 B read and 2106 (NCHW) / 81*c_stride (NHWC) elements written per game.
 // A block of 8 warps encodes 8 games.  Phase 1 builds the block's output as a packed BIT stream in shared

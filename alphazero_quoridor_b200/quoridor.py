@@ -125,9 +125,15 @@ class BatchedQuoridor:
                        "qz_env_sample_legal")
         return out
 
-    def random_play(self, seed=0, max_plies=3000, game_id=None, check_every=16):
-        """BASELINE config 1: uniform-random legal play to terminal with the FULL legal mask computed every ply
-        (legal_mask -> sample_actions -> step).  Returns the number of plies played per game (int64 [n])."""
+    def random_play(self, seed=0, max_plies=3000, game_id=None, fused=True, check_every=16):
+        """BASELINE config 1: uniform-random legal play to terminal with the FULL legal set computed every ply.
+        fused=True: two launches (qz_env_random_play); fused=False: the legal_mask -> sample_actions -> step loop,
+        which plays exactly the same games.  Returns the number of plies played per game (int64 [n])."""
+        if fused:
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.qz_env_random_play(_lib.ptr(self.states), int(seed) & M64, _lib.ptr(game_id),
+                                                       int(max_plies), self.n, self._stream()), "qz_env_random_play")
+            return (self.states[:, 2] >> 48) & 0xFFFF
         mask = torch.empty((self.n, 3), dtype=torch.int64, device=self.device)
         acts = torch.empty((self.n,), dtype=torch.int32, device=self.device)
         done = torch.empty((self.n,), dtype=torch.uint8, device=self.device)

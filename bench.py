@@ -479,10 +479,10 @@ def kernel_section(torch, dev, hbm_peak):
         out["qz_encode_kernel_" + name] = {"units": n2, "ms": ms, "bytes_per_unit": nb // n2,
                                            "achieved_GBps": nb / ms / 1e6, "frac_hbm": nb / ms / 1e6 / hbm_peak, "bound": "hbm"}
         del buf
-    # BASELINE config 1 literally: random games with the FULL legal mask computed every ply (3 launches per ply)
-    ng = 1 << 18
+    # BASELINE config 1 literally: random games from reset() to terminal, FULL legal set computed on every ply
+    ng = 1 << 20
     envg = BatchedQuoridor(ng, device=dev)
-    envg.random_play(seed=1, max_plies=48)
+    envg.random_play(seed=1, max_plies=3000)
     envg.reset()
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -493,7 +493,8 @@ def kernel_section(torch, dev, hbm_peak):
     ms = a.elapsed_time(b)
     out["random_play_full_mask"] = {"games": ng, "ms": ms, "env_steps_per_s": float(plies.sum().item()) / ms * 1e3,
                                     "mean_plies": float(plies.float().mean().item()),
-                                    "workload": "BASELINE config 1: reset() to terminal, legal_mask + sample_legal + step per ply"}
+                                    "workload": "BASELINE config 1: 2^20 games from reset() to terminal, full 140-action legal "
+                                                "set + uniform pick + step on every ply (qz_env_random_play, 2 launches)"}
     del envg
     n3 = 1 << 24     # 403 MB of states: larger than L2
     env3 = BatchedQuoridor(n3, device=dev)

@@ -109,6 +109,15 @@ int qz_env_sample_legal(const qz_state *states, const uint64_t *mask3, uint64_t 
                         int32_t *actions, int64_t n, void *stream);
 
 /*
+ * BASELINE config 1 in two launches: every game of `states` is played to its end (or until its ply counter reaches
+ * max_plies) by uniform-random legal moves, the FULL legal set being computed on every ply (Quoridor.actions +
+ * the pick of qz_env_sample_legal + Quoridor.step) -- the same games, ply for ply, as looping the three calls.
+ * A stalemated game gets its "stalemate" flag.  The ply counters in states[i].meta give the plies played.
+ */
+int qz_env_random_play(qz_state *states, uint64_t seed, const int64_t *game_id, int32_t max_plies, int64_t n,
+                       void *stream);
+
+/*
  * Quoridor.state (quoridor.py:58-131): the 26 x 9 x 9 planes of each game, written in `dtype`
  * straight into the policy-value net's input buffer.
  *   layout NCHW: out is [n][26][9][9].   layout NHWC: out is [n][9][9][c_stride], channels >= 26 zeroed.

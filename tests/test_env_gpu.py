@@ -302,3 +302,8 @@ def test_full_mask_random_games_vs_oracle(qz):
             pos["H"], pos["V"], pos["p1"], pos["p2"], pos["w1"], pos["w2"], pos["cur"])
         assert d["done"] == g.has_a_winner()[0] and d["winner"] == (g.has_a_winner()[1] or 0)
     assert 200 < plies.mean() < 500 and np.mean([d["done"] for d in hs]) > 0.97      # a few games hit the ply cap
+    # the three-launch-per-ply loop plays the very same games
+    env2 = qz.BatchedQuoridor(n)
+    plies2 = env2.random_play(seed=seed, max_plies=3000, game_id=gid, fused=False).cpu().numpy()
+    assert np.array_equal(plies, plies2) and torch.equal(env.states[:, :2], env2.states[:, :2])
+    assert torch.equal(env.states[:, 2] & 0xFFFFFFFFFF, env2.states[:, 2] & 0xFFFFFFFFFF)
