@@ -363,3 +363,44 @@ def test_reference_private_surface(qz, mcts_golden):
     assert set(vals) <= {-1, 0, 1} and h._positions == {1: 4, 2: 76}
     p._playout(h)
     assert abs(p._root._children[0]._P - 1.0 / 131) < 1e-15 and p._root._n_visits == 1
+
+
+def test_full_size_configs_properties(qz):
+    """BASELINE configs[1] and [2] at their full sizes, through properties that need no oracle plus a sampled
+    oracle check: every playout is counted exactly once, probabilities are a distribution over legal moves, chosen
+    moves are legal, nothing overflows, and the run is reproducible."""
+    from alphazero_quoridor_b200.selfplay import BatchedSelfPlay
+    # configs[2]: 8192 games, n_playout = 100, c_puct = 5 (deterministic stub as the evaluator, one leaf per wave)
+    n, npl = 8192, 100
+    states = _positions(n, seed=99, min_plies=0, max_plies=50)
+    eng = qz.tree.BatchedMCTS(n, qz.tree.StubEvaluator("S3"), c_puct=5, n_playout=npl, leaves_per_game=1, reuse_tree=False)
+    eng.reset(states)
+    eng.search()
+    visits, probs, rootn = eng.root_stats(temp=1.0)
+    assert (rootn == npl).all() and eng.overflow_count() == 0
+    tot = visits.sum(1)
+    assert ((tot == npl - 1) | (tot == 0)).all()
+    env = qz.q.BatchedQuoridor(n, states=states)
+    mask = env.legal_mask()
+    bits = torch.stack([(mask[:, a >> 6] >> (a & 63)) & 1 for a in range(140)], 1).bool()
+    assert not (visits[~bits] != 0).any()                                     # visits only on legal actions
+    np.testing.assert_allclose(probs.sum(1)[tot > 0].cpu().numpy(), 1.0, rtol=1e-12)
+    moves = eng.choose(mode=0)
+    ok = torch.gather(bits, 1, moves.clamp(min=0).long().unsqueeze(1)).squeeze(1) | (moves < 0)
+    assert ok.all()
+    idx = torch.arange(0, n, 128)
+    _, H, V, meta5 = _host(qz, states[idx.to(states.device)].clone())
+    _, want = O.stub_mcts_visits(H, V, meta5, npl, c_puct=5.0, stub_kind=3)
+    assert np.array_equal(visits[idx.to(visits.device)].cpu().numpy(), want)     # sampled exact check
+    # configs[1]: 4096 games, 1000 rollouts per move, 64 leaves per wave, stuck rollouts deferred
+    outs = []
+    for _ in range(2):
+        sp = BatchedSelfPlay(4096, qz.tree.RolloutEvaluator(seed=7), c_puct=5, n_playout=1000, leaves_per_game=64,
+                             pure=True, seed=7, defer_depth=4)
+        sp.mcts.search()
+        v, _, rn = sp.mcts.root_stats(temp=1.0)
+        assert (rn == 1000).all() and (v.sum(1) == 999).all() and sp.mcts.overflow_count() == 0
+        mv = sp.mcts.choose(mode=0)
+        outs.append((v.clone(), mv.clone()))
+        assert (v[0].nonzero().flatten().cpu().tolist() == sorted(qz.q.Quoridor().actions()))     # all 131 root moves tried
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
