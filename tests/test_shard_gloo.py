@@ -67,3 +67,46 @@ def test_two_rank_gloo_reduction_and_gather():
         assert ok_rows
         assert ms == 11.0                      # max over ranks
         assert work == [float(n_total), 2.0]   # sum over ranks
+
+
+def _train_worker(rank, ws, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        import numpy as np
+        from alphazero_quoridor_b200.policy_value_net import PolicyValueNet
+        from alphazero_quoridor_b200.train import allreduce_gradients
+        torch.manual_seed(0)
+        torch.set_num_threads(1)
+        net = PolicyValueNet(use_gpu=False)
+        rng = np.random.RandomState(5)
+        s = rng.randint(0, 2, size=(16, 26, 9, 9)).astype(np.float64)
+        p = rng.dirichlet(np.ones(140), size=16)
+        z = rng.choice([-1.0, 1.0], size=16)
+        lo, hi = rank * 8, rank * 8 + 8                       # each rank trains on its own half of the batch
+        params = list(net.policy_value_net.parameters())
+        net.train_step(s[lo:hi], p[lo:hi], z[lo:hi], 2e-3, grad_hook=lambda: allreduce_gradients(params))
+        flat = torch.cat([x.detach().reshape(-1) for x in params])
+        q.put((rank, flat.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_trainer_gradient_allreduce_two_ranks():
+    """The trainer's only collective (gradient averaging): two ranks on different half-batches end up with
+    identical weights (conv/linear weights; BatchNorm batch statistics are per rank, as with DDP)."""
+    ws = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_train_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=150) for _ in range(ws))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    import numpy as np
+    assert np.array_equal(res[0], res[1])
+    assert np.isfinite(res[0]).all()
