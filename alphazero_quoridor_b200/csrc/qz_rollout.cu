@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
             bool leave = qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0;
             if (!leave) {
                 const int act = qz_sample_action_capped(s, rng, (uint32_t)steps, QZ_MAX_REJECTS);
-                if (act == -2) {                                        // stuck: hand over to the block-per-rollout kernel
+                if (act == -2) {                                        // stuck: hand over to qz_rollout_stuck_kernel
                     const unsigned long long k = atomicAdd(a.counter + 3, 1ull);
                     a.stuck_list[k] = (int32_t)r;
                     s.meta |= (uint64_t)QZ_FLAG_PENDING << 40;

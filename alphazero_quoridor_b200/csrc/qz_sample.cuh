@@ -5,7 +5,7 @@
 // of quoridor.py:432-461} until the drawn element is legal -- a wall is legal iff the reference's path check
 // (quoridor.py:463-477) accepts it -- is the same distribution (rejection sampling) at ~1 path check per ply
 // instead of 128.  The procedure is specified exactly so that every implementation of it -- the per-lane
-// kernel path, the table-driven block path for stuck rollouts, and the oracle (oq_sample_action, built on the
+// kernel path, the warp-per-rollout path for stuck rollouts, and the oracle (oq_sample_action, built on the
 // literal actions()) -- returns the same action bit for bit:
 //   S is ordered: pawn ids ascending, then H candidates by intersection, then V candidates; M = |S|.
 //   attempt 0 of ply t  uses word (t & 3)       of Philox4x32-10(key = seed; ctr = (rid_lo, rid_hi, t >> 2, 0))
@@ -87,7 +87,8 @@ QZ_HD int qz_sample_action(const QzState &s, QzRng &rng, uint32_t ply) {
 }
 
 // The same attempt sequence when the legal walls (hl, vl) are already known (from a full sweep): legality is
-// a table lookup.  Identical result.  (The block kernel evaluates the attempts in parallel instead.)
+// a table lookup.  Identical result; kept as the sequential statement of the rule (host harness cross-check) --
+// qz_rollout_stuck_kernel evaluates 32 attempts at a time instead.
 QZ_HD int qz_sample_action_known(const QzState &s, QzRng &rng, uint32_t ply, uint32_t pmask, uint64_t hl, uint64_t vl) {
     uint64_t hc = 0, vc = 0;
     if (qz_mover_walls(s.meta) > 0) { hc = qz_hcand(s.H, s.V); vc = qz_vcand(s.H, s.V); }

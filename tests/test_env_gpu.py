@@ -254,8 +254,8 @@ def test_full_size_properties(qz):
 
 def test_stuck_rollouts_vs_oracle(qz):
     """Late positions where a player still owns walls but (nearly) none can be placed legally: these rollouts
-    leave the per-lane kernel and run in the block-per-rollout kernel with memoised backward floods
-    (qz_rollout_stuck_kernel).  Same Philox streams => value, plies and final position equal the oracle's."""
+    leave the per-lane kernel and run in the warp-per-rollout kernel (qz_rollout_stuck_kernel: 32 draw attempts
+    decoded at once, only the wall attempts before the first pawn attempt path-checked).  Same Philox streams => value, plies and final position equal the oracle's."""
     from alphazero_quoridor_b200.rollout import rollout
     from alphazero_quoridor_b200.synthetic import midgame_positions
     pos = midgame_positions(60000, seed=123, min_plies=28, max_plies=70)
