@@ -307,3 +307,26 @@ def test_full_mask_random_games_vs_oracle(qz):
     plies2 = env2.random_play(seed=seed, max_plies=3000, game_id=gid, fused=False).cpu().numpy()
     assert np.array_equal(plies, plies2) and torch.equal(env.states[:, :2], env2.states[:, :2])
     assert torch.equal(env.states[:, 2] & 0xFFFFFFFFFF, env2.states[:, 2] & 0xFFFFFFFFFF)
+
+
+def test_facade_replays_golden_traces(qz, traces):
+    """The drop-in single-game class, call for call as the reference is used: actions() / state() / step() on
+    whole recorded games (one per action policy)."""
+    picked = [next(t for t in traces if t["policy"] == pol) for pol in ("uniform", "wallmix", "forward")]
+    for tr in picked:
+        g = qz.Quoridor()
+        for rec in tr["plies"][:260]:
+            assert g.actions() == rec["actions"]
+            assert g.get_current_player() == rec["cur"]
+            assert (g._positions[1], g._positions[2]) == (rec["p1"], rec["p2"])
+            assert (g._player1_walls_remaining, g._player2_walls_remaining) == (rec["w1"], rec["w2"])
+            if rec["state"] is not None and rec is tr["plies"][0] or rec["action"] is None:
+                s = g.state()
+                assert hashlib.sha256(s.astype(np.uint8).tobytes()).hexdigest() == rec["state"]
+            if rec["action"] is None:
+                break
+            done = g.step(rec["action"])
+            assert g.valid_actions == rec["actions"]                       # step() refreshes it (quoridor.py:165)
+        if len(tr["plies"]) <= 260:
+            fin = tr["final"]
+            assert done == fin["done"] and g.has_a_winner() == (fin["done"], fin["winner"] or None)
