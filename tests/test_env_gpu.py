@@ -313,9 +313,11 @@ def test_facade_replays_golden_traces(qz, traces):
     """The drop-in single-game class, call for call as the reference is used: actions() / state() / step() on
     whole recorded games (one per action policy)."""
     picked = [next(t for t in traces if t["policy"] == pol) for pol in ("uniform", "wallmix", "forward")]
+    replayed = 0
     for tr in picked:
         g = qz.Quoridor()
         for rec in tr["plies"][:260]:
+            replayed += 1
             assert g.actions() == rec["actions"]
             assert g.get_current_player() == rec["cur"]
             assert (g._positions[1], g._positions[2]) == (rec["p1"], rec["p2"])
@@ -330,3 +332,4 @@ def test_facade_replays_golden_traces(qz, traces):
         if len(tr["plies"]) <= 260:
             fin = tr["final"]
             assert done == fin["done"] and g.has_a_winner() == (fin["done"], fin["winner"] or None)
+    assert replayed > 300
