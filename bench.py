@@ -343,7 +343,11 @@ def run_ours(args):
     achieved = bytes_per_rollout * avg_n / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
     roofline = {"kernel": "qz_rollout_wall_kernel + qz_rollout_pawn_kernel (main stream) + qz_rollout_stuck_kernel (side stream)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / hbm_peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of the three kernels in profiles/r1g_rollout_ncu_full.txt
+                # (one 262,144-rollout launch: 0.7 + 0.2 + 6.3 MB), scaled to this run's rollouts per launch; it is BELOW
+                # the algorithmic 85 B/rollout because the 126 MB L2 absorbs the 48 B/rollout phase hand-over buffer
+                "traffic": 7.2e6 * avg_n / 262144.0, "peak_source": peak_src,
                 "launches_timed": len(roll_ms), "avg_launch_ms": avg_ms, "avg_main_stream_ms": avg_main,
                 "avg_deferred_stuck_pass_ms": avg_stuck, "rollouts_per_launch": avg_n,
                 "share_of_step": (sum(roll_ms) + sum(stuck_ms)) / ms if ms > 0 else None,
