@@ -62,3 +62,30 @@ def test_no_cpu_fallback_without_gpu(so_path):
     g = Quoridor()            # pure host attributes, constructing is fine
     with pytest.raises(_lib.QzError):
         g.actions()           # ... but any rules query needs the device
+
+
+def test_more_argument_errors_need_no_gpu(so_path):
+    """Every entry point validates its arguments before touching CUDA (return < 0, message set)."""
+    import ctypes as C
+    from alphazero_quoridor_b200 import _lib, tree
+    lib = _lib.load()
+    p8 = C.c_void_p(64)
+    # rollouts
+    assert lib.qz_rollout(None, 0, None, 1, 0, 0, 0, None, 1000, None, None, None, None, 0, None) == 0      # empty
+    assert lib.qz_rollout(None, 4, None, 1, 4, 0, 0, None, 1000, p8, None, None, p8, 0, None) == -1          # states NULL
+    assert lib.qz_rollout(p8, 4, None, 1, 4, 0, 0, None, 0, p8, None, None, p8, 0, None) == -2               # limit < 1
+    assert lib.qz_rollout(p8, 2, None, 1, 4, 0, 0, None, 1000, p8, None, None, p8, 0, None) == -2            # 2 states x 1 < 4
+    assert lib.qz_rollout(C.c_void_p(68), 4, None, 1, 4, 0, 0, None, 1000, p8, None, None, p8, 0, None) == -3
+    assert lib.qz_rollout_workspace_bytes(1000) >= 64 + 1000 * 24 + 4000
+    assert lib.qz_env_random_play(None, 0, None, 3000, 5, None) == -1
+    assert lib.qz_env_random_play(p8, 0, None, 70000, 5, None) == -2
+    assert lib.qz_env_sample_legal(p8, None, 0, None, p8, 5, None) == -1
+    # trees
+    t = tree.QzTree()
+    assert lib.qz_mcts_init(None, None, None, None) == -1
+    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, None) == -2                                            # zero dimensions
+    t.n_games, t.node_cap, t.max_depth, t.leaves_per_game = 4, 100, 16, 2
+    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, None) == -1                                            # arrays NULL
+    assert b"NULL" in lib.qz_last_error_string()
+    assert lib.qz_stub_eval(p8, p8, 9, p8, p8, 4, None) == -2                                                # unknown stub kind
+    assert lib.qz_device_sm_count(None) == -1
