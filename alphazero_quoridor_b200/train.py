@@ -43,6 +43,36 @@ def allreduce_gradients(parameters):
         off += n
 
 
+# ---- left-right mirror symmetry ------------------------------------------------------------------
+# tile (r,c) -> (r,8-c); intersection (r,c) -> (r,7-c); pawn actions E<->W, EE<->WW, NE<->NW, SE<->SW.  The commented-out
+# get_equi_data of train.py:40-53 is Gomoku-shaped and wrong for Quoridor; this is the symmetry the board really has.
+# NOTE the reference's row-0 corner aliasing (quoridor.py:388,:392) is itself mirror-asymmetric, so a mirrored position
+# is only approximately equivalent under the reference's rules (exactly equivalent away from row 0).
+_MIRROR_PAWN = [0, 1, 3, 2, 4, 5, 7, 6, 9, 8, 11, 10]
+MIRROR_ACTION = torch.tensor(_MIRROR_PAWN + [12 + (ix // 8) * 8 + (7 - ix % 8) for ix in range(64)]
+                             + [76 + (ix // 8) * 8 + (7 - ix % 8) for ix in range(64)], dtype=torch.int64)
+
+
+def _mirror_mask64(m):
+    """Reverse the 8 columns inside every row of an 8x8 bit mask held in int64 tensors (byte-wise bit reversal)."""
+    m = ((m >> 1) & 0x5555555555555555) | ((m & 0x5555555555555555) << 1)
+    m = ((m >> 2) & 0x3333333333333333) | ((m & 0x3333333333333333) << 2)
+    m = ((m >> 4) & 0x0F0F0F0F0F0F0F0F) | ((m & 0x0F0F0F0F0F0F0F0F) << 4)
+    return m
+
+
+def mirror_samples(states, probs):
+    """Left-right mirrored copies of self-play samples: states int64 [m,3] (qz_state rows with on-board pawns), probs
+    [m,140].  z is unchanged by the symmetry."""
+    H, V, meta = states[:, 0], states[:, 1], states[:, 2]
+    p1, p2 = meta & 0xFF, (meta >> 8) & 0xFF
+    p1m = (p1 // 9) * 9 + (8 - p1 % 9)
+    p2m = (p2 // 9) * 9 + (8 - p2 % 9)
+    meta_m = (meta & ~0xFFFF) | p1m | (p2m << 8)
+    out = torch.stack([_mirror_mask64(H), _mirror_mask64(V), meta_m], 1)
+    return out, probs[:, MIRROR_ACTION.to(probs.device)]
+
+
 class TrainPipeline(object):
     def __init__(self, init_model=None, n_parallel_games=256, leaves_per_game=4, device=None, seed=0,
                  fix_terminal_sign=False, max_plies=600):
@@ -130,6 +160,62 @@ class TrainPipeline(object):
                                explained_var_old=float(1 - np.var(winner_batch - old_v.flatten()) / var) if var > 0 else 0.0,
                                explained_var_new=float(1 - np.var(winner_batch - new_v.flatten()) / var) if var > 0 else 0.0)
         return loss, entropy
+
+    # ---- checkpoint / resume ----
+    def save_checkpoint(self, path, model_name=None):
+        """Everything needed to resume: the net (also written in the reference's own format, ckpt/<name>.pth, when
+        `model_name` is given: policy_value_net.py:198-200), plus what the reference does not save -- optimizer state,
+        learning-rate multiplier and the replay buffer."""
+        if model_name:
+            self.policy_value_net.save_model(model_name)
+        buf = list(self.data_buffer)
+        torch.save({"net": self.policy_value_net.get_policy_param(),
+                    "optimizer": self.policy_value_net.optimizer.state_dict(),
+                    "lr_multiplier": self.lr_multiplier,
+                    "buffer_states": torch.stack([b[0] for b in buf]) if buf else torch.zeros((0, 3), dtype=torch.int64),
+                    "buffer_probs": torch.stack([b[1] for b in buf]) if buf else torch.zeros((0, 140)),
+                    "buffer_z": torch.tensor([b[2] for b in buf], dtype=torch.float32)}, path)
+
+    def load_checkpoint(self, path):
+        ck = torch.load(path, map_location=self.policy_value_net.device)
+        self.policy_value_net.policy_value_net.load_state_dict(ck["net"])
+        self.policy_value_net.optimizer.load_state_dict(ck["optimizer"])
+        self.policy_value_net._infer = None
+        self.lr_multiplier = ck["lr_multiplier"]
+        self.data_buffer.clear()
+        self.data_buffer.extend(zip(ck["buffer_states"].cpu().unbind(0), ck["buffer_probs"].cpu().unbind(0),
+                                    ck["buffer_z"].tolist()))
+
+    # ---- evaluation arena (SURVEY.md 8f.3; the commented-out policy_evaluate of train.py:30-31,108) ----
+    def policy_evaluate(self, n_games=64, n_playout=None, max_plies=300, seed=0):
+        """Win ratio of the current net's MCTS player against pure MCTS (`pure_mcts_playout_num` rollouts per move),
+        all games played side by side on the device; the net plays first in even games, second in odd ones.  Both
+        sides search with the corrected terminal sign (a player that avoids winning moves cannot be rated)."""
+        from .tree import BatchedMCTS, RolloutEvaluator
+        dev = self.policy_value_net.device
+        npl = self.n_playout if n_playout is None else n_playout
+        az = BatchedMCTS(n_games, NetEvaluator(self.policy_value_net), c_puct=self.c_puct, n_playout=npl,
+                         leaves_per_game=self.leaves_per_game, reuse_tree=False, fix_terminal_sign=True, device=dev)
+        pure = BatchedMCTS(n_games, RolloutEvaluator(seed=seed), c_puct=5, n_playout=self.pure_mcts_playout_num,
+                           leaves_per_game=16, reuse_tree=False, fix_terminal_sign=True, device=dev)
+        env = BatchedQuoridor(n_games, device=dev)
+        az_color = (torch.arange(n_games, device=dev) % 2) + 1               # 1: net moves first, 2: second
+        for ply in range(max_plies):
+            meta = env.states[:, 2]
+            if bool((((meta >> 40) & 1) == 1).all()):
+                break
+            az.reset(env.states)
+            az.search()
+            pure.reset(env.states)
+            pure.search()
+            mover = (meta >> 32) & 0xFF
+            moves = torch.where(mover == az_color, az.choose(mode=0), pure.choose(mode=0))
+            env.step(moves)
+        meta = env.states[:, 2]
+        winner = (meta >> 41) & 3
+        wins = (winner == az_color).sum().item()
+        ties = (winner == 0).sum().item()
+        return (wins + 0.5 * ties) / n_games
 
     def run(self):
         """train.py:94-111"""

@@ -58,3 +58,54 @@ def test_train_pipeline_collects_and_updates():
     assert st.shape == (3,) and pr.shape == (140,) and z in (-1.0, 0.0, 1.0)
     loss, entropy = tp.policy_update()
     assert np.isfinite(loss) and np.isfinite(entropy) and 0.1 <= tp.lr_multiplier <= 10
+
+
+def test_mirror_augmentation():
+    """Left-right mirror of (state, probs): planes flip left-right, wall planes flip inside their 8x8 block, action
+    probabilities follow the action permutation; mirroring twice is the identity."""
+    from alphazero_quoridor_b200.quoridor import BatchedQuoridor
+    from alphazero_quoridor_b200.synthetic import midgame_positions
+    from alphazero_quoridor_b200.train import MIRROR_ACTION, mirror_samples
+    st = midgame_positions(512, seed=2, min_plies=0, max_plies=60)
+    probs = torch.rand(512, 140, device=st.device)
+    m_st, m_pr = mirror_samples(st, probs)
+    back_st, back_pr = mirror_samples(m_st, m_pr)
+    assert torch.equal(back_st, st) and torch.equal(back_pr, probs)
+    assert sorted(MIRROR_ACTION.tolist()) == list(range(140))
+    a = BatchedQuoridor(512, states=st.clone()).encode()
+    b = BatchedQuoridor(512, states=m_st.clone()).encode()
+    assert torch.equal(b[:, 3:], a[:, 3:].flip(3))                              # pawn / wall-count / turn planes
+    assert torch.equal(b[:, :3, :8, :8], a[:, :3, :8, :8].flip(3))              # wall planes: 8x8 block mirrored
+    # away from row 0 the mirrored position has exactly the mirrored legal moves
+    env_a, env_b = BatchedQuoridor(512, states=st.clone()), BatchedQuoridor(512, states=m_st.clone())
+    la, lb = env_a.legal_lists(), env_b.legal_lists()
+    perm = MIRROR_ACTION.tolist()
+    hs = env_a.host_states()
+    checked = 0
+    for i in range(512):
+        d = hs[i]
+        if d["p1"] >= 18 and d["p2"] >= 18 and (d["H"] | d["V"]) & 0xFF == 0:    # nothing on row 0 / its intersections
+            assert sorted(perm[x] for x in la[i]) == sorted(lb[i])
+            checked += 1
+    assert checked > 5
+
+
+def test_checkpoint_resume_and_arena(tmp_path):
+    from alphazero_quoridor_b200.train import TrainPipeline
+    torch.manual_seed(0)
+    tp = TrainPipeline(n_parallel_games=64, leaves_per_game=4, fix_terminal_sign=True, max_plies=120)
+    tp.n_playout = 12
+    tp.collect_selfplay_data(2)
+    tp.policy_update()
+    path = str(tmp_path / "resume.pt")
+    tp.save_checkpoint(path)
+    tp2 = TrainPipeline(n_parallel_games=64, leaves_per_game=4, fix_terminal_sign=True, max_plies=120)
+    tp2.load_checkpoint(path)
+    for (k, a), (_, b) in zip(tp.policy_value_net.get_policy_param().items(), tp2.policy_value_net.get_policy_param().items()):
+        assert torch.equal(a, b), k
+    assert len(tp2.data_buffer) == len(tp.data_buffer) and tp2.lr_multiplier == tp.lr_multiplier
+    assert torch.equal(tp2.data_buffer[3][0], tp.data_buffer[3][0]) and tp2.data_buffer[3][2] == tp.data_buffer[3][2]
+    # arena: a random-init net against pure MCTS with a few rollouts -- just has to run and return a ratio
+    tp2.pure_mcts_playout_num = 24
+    ratio = tp2.policy_evaluate(n_games=16, n_playout=8, max_plies=80)
+    assert 0.0 <= ratio <= 1.0
