@@ -20,14 +20,17 @@ __device__ __forceinline__ uint64_t qz_warp_or64(uint64_t x) {
 #define QZ_WITNESS_MAX_DEPTH 48
 #define QZ_WARP_SCRATCH_WORDS (2 * QZ_WITNESS_MAX_DEPTH * 3 + 128)     // two layer stacks + 256 u16 tasks
 
+// Called by a whole half-warp with identical arguments: one lane stores the layers, all lanes read them back.
 __device__ __forceinline__ bool qz_witness_path(const QzDirs &d, int start, int O, int player, uint32_t *layers, BB &path) {
+    const bool writer = (threadIdx.x & 15) == 0;
+    const unsigned half = (threadIdx.x & 16) ? 0xFFFF0000u : 0x0000FFFFu;
     BB reach = bb_bit(start);
     BB keep = bb_bit(O);
     keep.w0 = ~keep.w0; keep.w1 = ~keep.w1; keep.w2 = ~keep.w2;
     int depth = 0;
     path = bb_zero();
     for (;;) {
-        layers[3 * depth] = reach.w0; layers[3 * depth + 1] = reach.w1; layers[3 * depth + 2] = reach.w2;
+        if (writer) { layers[3 * depth] = reach.w0; layers[3 * depth + 1] = reach.w1; layers[3 * depth + 2] = reach.w2; }
         const BB a = bb_shl(bb_and(reach, d.n), 9), b = bb_shr(bb_and(reach, d.s), 9);
         const BB c = bb_shl(bb_and(reach, d.e), 1), e = bb_shr(bb_and(reach, d.w), 1);
         BB nxt;
@@ -39,6 +42,7 @@ __device__ __forceinline__ bool qz_witness_path(const QzDirs &d, int start, int 
             // walk back: u is on layer depth+1, find a tile of layer `depth` with an open move onto u
             int u = player == 1 ? 64 + (__ffs(hit) - 1) : __ffs(hit) - 1;
             path = bb_bit(u);
+            __syncwarp(half);
             for (int k = depth; k >= 0; k--) {
                 // tiles at distance exactly k: a tile at distance k+1 always has a predecessor among them
                 BB L = bb_make(layers[3 * k], layers[3 * k + 1], layers[3 * k + 2]);
