@@ -39,6 +39,11 @@ def pawn_cases():
     return load_golden("pawn_cases.json.gz")
 
 
+def n_mcts_golden():
+    """number of recorded mcts.MCTS runs (for parametrize at collection time)"""
+    return len(load_golden("mcts_golden.json"))
+
+
 @pytest.fixture(scope="session")
 def mcts_golden():
     return load_golden("mcts_golden.json")

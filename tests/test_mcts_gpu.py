@@ -9,6 +9,7 @@ import numpy as np
 import pytest
 import torch
 
+from conftest import n_mcts_golden
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -42,11 +43,9 @@ def _facade(qz, pos):
     return g
 
 
-@pytest.mark.parametrize("idx", range(40))
+@pytest.mark.parametrize("idx", range(n_mcts_golden()))
 def test_mcts_golden_reference_api(qz, mcts_golden, idx):
     """mcts.MCTS(policy, c_puct, n).get_move_probs / update_with_move vs the recorded reference runs."""
-    if idx >= len(mcts_golden):
-        pytest.skip("no such case")
     case = mcts_golden[idx]
     tree = qz.mcts.MCTS(qz.mcts.DeviceStub(case["stub"]), case["c_puct"], case["n_playout"])
     g = _facade(qz, case["moves"][0]["pos"])

@@ -8,6 +8,7 @@ import hashlib
 import numpy as np
 import pytest
 
+from conftest import n_mcts_golden
 from oracle import oracle as O
 
 
@@ -87,11 +88,9 @@ def test_offboard_terminal():
         g.state()
 
 
-@pytest.mark.parametrize("idx", range(64))
+@pytest.mark.parametrize("idx", range(n_mcts_golden()))
 def test_mcts_golden(mcts_golden, idx):
     """mcts.py:103-151 under the deterministic stubs: visit vectors, Q and probabilities."""
-    if idx >= len(mcts_golden):
-        pytest.skip("no such case")
     case = mcts_golden[idx]
     kind = {"S1": 1, "S2": 2, "S3": 3}[case["stub"]]
     tree = O.OracleMCTS(kind, case["c_puct"], case["n_playout"])
