@@ -6,10 +6,10 @@
 // immediately claims the next unstarted rollout from a global counter (warp-aggregated atomicAdd) and the
 // warp stays converged at the top of one "advance every live lane by one ply" loop.  A rollout is cut in two
 // PHASES run by two kernels -- plies while walls remain (flood fills, ~2000 instructions each) and pawn-only
-// plies (~150 instructions each) -- so that the lanes of a warp always execute the same kind of ply; the
+// plies (~140 instructions each) -- so that the lanes of a warp always execute the same kind of ply; the
 // first capture (profiles/r1a_rollout_ncu_full.txt) of the single-kernel form showed 4.2 active lanes per
-// instruction because a warp mixed both kinds.  No tensor cores, no shared memory: the game lives in
-// registers and HBM sees 24 B in, 48 B through `mid`, and 1..29 B out per ROLLOUT.
+// instruction because a warp mixed both kinds.  No tensor cores: the game lives in registers (the pawn phase
+// adds a byte-per-tile table in shared memory) and HBM sees 24 B in, 48 B through `mid`, 1..29 B out per ROLLOUT.
 #include "qz_common.cuh"
 #include "qz_sample.cuh"
 #include "qz_warp.cuh"
@@ -182,68 +182,139 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs 
 }
 
 // ---- phase 2: the pawn phase ------------------------------------------------------------------------------
-// No wall can be placed any more, so the twelve corner masks of the position are built ONCE per rollout and
-// every remaining ply is a branch-free pawn-move query, one Philox word, a nth-set-bit pick and a position
-// update: all 32 lanes of a warp run the same ~150 instructions per ply whatever tile they stand on.
-__global__ void __launch_bounds__(128) qz_rollout_pawn_kernel(QzRolloutArgs a) {
-    const int lane = threadIdx.x & 31;
-    QzState s;
-    QzRng rng;
-    QzPawnCtx ctx;
+// No wall can be placed any more, so everything the move rules read about a tile is constant for the rest of the
+// rollout.  When a lane takes a rollout it builds the twelve corner masks once and transposes eight of them into a
+// byte-per-tile table in shared memory (qz_tile_table; the four "corner is horizontal" masks, only read on an
+// east / west contact with the opponent, are parked as they are).  A ply is then: ONE table byte for the tile
+// the pawn just moved to (the other pawn's byte is carried over from the previous ply), a handful of bit
+// operations, one Philox word, the k-th set bit, an add -- about 90 instructions, whatever tiles the lanes stand
+// on -- instead of the ~350 of the generic state machine (profiles/r1g_rollout_ncu_full.txt: this kernel was 56 %
+// of all rollout instructions, 17.7 active lanes per instruction because refills ran one lane at a time).
+// Refills are batched: idle lanes wait until QZ_PAWN_REFILL of them can set up together.
+#define QZ_PAWN_THREADS 128
+#define QZ_PAWN_REFILL 8
+
+struct QzPawnSmem {
+    uint32_t tile[QZ_PAWN_THREADS * QZ_TILE_TABLE_WORDS];   // thread-major: byte t of thread i at i*84 + t
+    uint32_t hmask[12 * QZ_PAWN_THREADS];                   // word-major: neH, nwH, seH, swH x 3 words
+    int32_t delta[12];
+};
+
+__device__ __forceinline__ int8_t qz_pawn_result(int winner, int player0) {       // pure_mcts.py:104-108
+    return (int8_t)(winner == 0 ? 0 : (winner == player0 ? 1 : -1));
+}
+
+__global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzRolloutArgs a) {
+    __shared__ QzPawnSmem sm;
+    const int tid = threadIdx.x;
+    if (tid < 12) sm.delta[tid] = qz_delta(tid);
+    __syncthreads();
+    const uint8_t *my_tile = reinterpret_cast<const uint8_t *>(sm.tile + tid * QZ_TILE_TABLE_WORDS);
+    unsigned long long *work = a.list_mode ? a.counter + 5 : a.counter + 2;
+    const int64_t total = a.list_mode ? (int64_t)a.counter[3] : a.n_rollouts;
+    QzRng rng = qz_rng_init(0, 0);
     int64_t r = -1;
-    int player0 = 0, steps = 0;
+    int L = 0, O = 0, mover = 1, steps = 0, steps0 = 0, player0 = 0;
+    uint32_t iL = 0, iO = 0;
     unsigned long long my_plies = 0;
     bool exhausted = false;
-    s.H = s.V = s.meta = 0;
-    rng = qz_rng_init(0, 0);
-    ctx = qz_ctx_build(0, 0);
     for (;;) {
         const bool want = (r < 0) && !exhausted;
-        int64_t got = qz_claim(a.list_mode ? a.counter + 5 : a.counter + 2, want,
-                               a.list_mode ? (int64_t)a.counter[3] : a.n_rollouts);
-        if (want) {
-            if (got >= 0 && a.list_mode) got = a.stuck_list[got];
-            if (got >= 0) {
-                r = got;
-                s = qz_load_state(a.mid + r);
-                const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, r)) + 2);
+        const unsigned want_lanes = __ballot_sync(QZ_FULL_MASK, want);
+        const unsigned busy_lanes = __ballot_sync(QZ_FULL_MASK, r >= 0);
+        if (want_lanes && (busy_lanes == 0 || __popc(want_lanes) >= QZ_PAWN_REFILL)) {
+            // claim until every wanting lane holds a LIVE pawn-phase rollout (or the work is gone); rollouts that
+            // already ended in the wall phase, or are parked for the stuck kernel, are settled on the spot
+            bool need = want, fresh = false;
+            uint64_t H = 0, V = 0;
+            while (__any_sync(QZ_FULL_MASK, need)) {
+                int64_t got = qz_claim(work, need, total);
+                if (!need) continue;
+                if (got >= 0 && a.list_mode) got = a.stuck_list[got];
+                if (got < 0) { exhausted = true; need = false; continue; }
+                const QzState s = qz_load_state(a.mid + got);
+                const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, got)) + 2);
+                const unsigned fl = qz_flags(s.meta);
+                const int st = (int)qz_ply(s.meta) - (int)qz_ply(m0);
+                if (fl & QZ_FLAG_PENDING) {                  // deferred: finished later by qz_rollout_finish
+                    a.result[got] = (int8_t)-128;
+                    continue;
+                }
+                if ((fl & (QZ_FLAG_DONE | QZ_FLAG_STALEMATE)) || st >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) != 0 ||
+                    !qz_on_board(s.meta)) {                  // walls left here only if phase 1 ended the rollout
+                    a.result[got] = qz_pawn_result(qz_winner(s.meta), qz_cur(m0));
+                    if (a.plies) a.plies[got] = st;
+                    if (a.final_states) qz_store_state(a.final_states + got, s);
+                    my_plies += (unsigned long long)st;
+                    continue;
+                }
+                r = got; need = false; fresh = true;
+                H = s.H; V = s.V;
+                mover = qz_cur(s.meta);
+                L = mover == 1 ? qz_p1(s.meta) : qz_p2(s.meta);
+                O = mover == 1 ? qz_p2(s.meta) : qz_p1(s.meta);
+                steps = steps0 = st;
                 player0 = qz_cur(m0);
-                steps = (int)qz_ply(s.meta) - (int)qz_ply(m0);
-                rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + r) : a.rid_base + (uint64_t)r);
-                ctx = qz_ctx_build(s.H, s.V);
-            } else {
-                exhausted = true;
+                rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + got) : a.rid_base + (uint64_t)got);
             }
-        }
-        if (__all_sync(QZ_FULL_MASK, r < 0)) break;
-        if (r >= 0 && (qz_flags(s.meta) & QZ_FLAG_PENDING)) {
-            a.result[r] = (int8_t)-128;            // deferred: finished later by qz_rollout_finish
-            r = -1;
+            if (fresh) {
+                const QzPawnCtx c = qz_ctx_build(H, V);
+                qz_tile_table(c, sm.tile + tid * QZ_TILE_TABLE_WORDS, 1);
+                uint32_t *hm = sm.hmask + tid;
+                hm[0 * QZ_PAWN_THREADS] = c.neH.w0; hm[1 * QZ_PAWN_THREADS] = c.neH.w1; hm[2 * QZ_PAWN_THREADS] = c.neH.w2;
+                hm[3 * QZ_PAWN_THREADS] = c.nwH.w0; hm[4 * QZ_PAWN_THREADS] = c.nwH.w1; hm[5 * QZ_PAWN_THREADS] = c.nwH.w2;
+                hm[6 * QZ_PAWN_THREADS] = c.seH.w0; hm[7 * QZ_PAWN_THREADS] = c.seH.w1; hm[8 * QZ_PAWN_THREADS] = c.seH.w2;
+                hm[9 * QZ_PAWN_THREADS] = c.swH.w0; hm[10 * QZ_PAWN_THREADS] = c.swH.w1; hm[11 * QZ_PAWN_THREADS] = c.swH.w2;
+                iL = my_tile[L];
+                iO = my_tile[O];
+            }
+        } else if (busy_lanes == 0) {
+            break;
         }
         if (r >= 0) {
-            const unsigned fl = qz_flags(s.meta);
-            bool finished = (fl & (QZ_FLAG_DONE | QZ_FLAG_STALEMATE)) || steps >= a.limit - 1 ||
-                            (qz_w1(s.meta) + qz_w2(s.meta)) != 0;   // walls left here only if phase 1 ended the rollout
-            if (!finished) {
-                const uint32_t pm = qz_mover_pawn_moves_ctx(ctx, s.meta);
-                const int np = __popc(pm);
-                if (np == 0) {
-                    s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40;
+            // one ply (quoridor.py:146,159-186 with no wall left; pure_mcts.py:7-10,97-103)
+            uint32_t hO = 0;
+            if (qz_pawn_contact(iL, L, O) & 0xCu) {          // east / west contact: the opponent's H corners matter
+                const uint32_t *hm = sm.hmask + (O >> 5) * QZ_PAWN_THREADS + tid;
+                const int sh = O & 31;
+                hO = ((hm[0] >> sh) & 1u) | (((hm[3 * QZ_PAWN_THREADS] >> sh) & 1u) << 1) |
+                     (((hm[6 * QZ_PAWN_THREADS] >> sh) & 1u) << 2) | (((hm[9 * QZ_PAWN_THREADS] >> sh) & 1u) << 3);
+            }
+            uint32_t pm = qz_pawn_moves_info(iL, iO, hO, L, O, mover);
+            const int np = __popc(pm);
+            int winner = 0;
+            unsigned add_flags = 0;
+            bool finished = false;
+            if (np == 0) {
+                add_flags = QZ_FLAG_STALEMATE;
+                finished = true;
+            } else {
+                const uint32_t word = qz_rng_first_word(rng, (uint32_t)steps);
+                for (int k = (int)__umulhi(word, (uint32_t)np); k > 0; k--) pm &= pm - 1;      // drop the k lowest moves
+                L += sm.delta[__ffs(pm) - 1];                                                   // quoridor.py:217-243
+                steps++;
+                if (mover == 1 ? L > 71 : L < 9) {            // :193-202; the mover is not rotated on a win (:176-181)
+                    winner = mover;
+                    add_flags = QZ_FLAG_DONE | ((unsigned)winner << QZ_FLAG_WINNER_SHIFT);
                     finished = true;
                 } else {
-                    const uint32_t word = qz_rng_first_word(rng, (uint32_t)steps);
-                    const int k = (int)__umulhi(word, (uint32_t)np);
-                    const int act = (int)__fns(pm, 0, k + 1);
-                    s = qz_apply(s, act);
-                    steps++;
-                    finished = qz_done(s.meta) || steps >= a.limit - 1;
+                    const int t = L; L = O; O = t;
+                    const uint32_t moved = my_tile[O];
+                    iL = iO; iO = moved;
+                    mover = 3 - mover;
+                    finished = steps >= a.limit - 1;
                 }
             }
             if (finished) {
-                const int winner = qz_winner(s.meta);
-                a.result[r] = (int8_t)(winner == 0 ? 0 : (winner == player0 ? 1 : -1));     // pure_mcts.py:104-108
+                a.result[r] = qz_pawn_result(winner, player0);
                 if (a.plies) a.plies[r] = steps;
-                if (a.final_states) qz_store_state(a.final_states + r, s);
+                if (a.final_states) {
+                    QzState s = qz_load_state(a.mid + r);
+                    const unsigned ply = qz_ply(s.meta) + (unsigned)(steps - steps0);
+                    s.meta = qz_pack_meta(mover == 1 ? L : O, mover == 1 ? O : L, 0, 0, mover, qz_flags(s.meta) | add_flags,
+                                          ply < 0xFFFFu ? ply : 0xFFFFu);
+                    qz_store_state(a.final_states + r, s);
+                }
                 my_plies += (unsigned long long)steps;
                 r = -1;
             }
@@ -252,7 +323,7 @@ __global__ void __launch_bounds__(128) qz_rollout_pawn_kernel(QzRolloutArgs a) {
     // cumulative env-step counter (workspace word 1; never zeroed by the library)
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) my_plies += __shfl_xor_sync(QZ_FULL_MASK, my_plies, off);
-    if (lane == 0 && my_plies) atomicAdd(a.counter + 1, my_plies);
+    if ((tid & 31) == 0 && my_plies) atomicAdd(a.counter + 1, my_plies);
 }
 
 extern "C" int64_t qz_rollout_workspace_bytes(int64_t n_rollouts) {
@@ -313,7 +384,8 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
         rc = qz_check_launch("qz_rollout (stuck phase)");
         if (rc) return rc;
     }
-    qz_rollout_pawn_kernel<<<qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, 128), 128, 0, st>>>(a);
+    qz_rollout_pawn_kernel<<<qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, QZ_PAWN_THREADS),
+                             QZ_PAWN_THREADS, 0, st>>>(a);
     return qz_check_launch("qz_rollout (pawn phase)");
 }
 
@@ -333,7 +405,7 @@ extern "C" int qz_rollout_finish(const qz_state *states, int64_t n_states, const
     if (rc) return rc;
     a.list_mode = 1;
     // the deferred list is short (well under 1 % of the rollouts): a quarter of a resident wave is plenty
-    int blocks = qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, 128) / 4;
-    qz_rollout_pawn_kernel<<<blocks > 0 ? blocks : 1, 128, 0, st>>>(a);
+    int blocks = qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, QZ_PAWN_THREADS) / 4;
+    qz_rollout_pawn_kernel<<<blocks > 0 ? blocks : 1, QZ_PAWN_THREADS, 0, st>>>(a);
     return qz_check_launch("qz_rollout_finish (pawn phase)");
 }

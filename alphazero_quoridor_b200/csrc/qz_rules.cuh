@@ -381,6 +381,67 @@ QZ_HD uint32_t qz_pawn_moves_ctx(const QzPawnCtx &c, int L, int O, int player) {
     return m;
 }
 
+// ---- per-tile info bytes (pawn-only play) --------------------------------------------------------------------
+// When no wall can be placed any more the walls are constant, so everything quoridor.py:272-353 reads about a tile
+// is eight bits: bit 0..3 = plain move N,S,E,W open (d.n/s/e/w), bit 4..7 = corner NE,NW,SE,SW is a VERTICAL wall.
+// Byte t of an 84-byte table (21 words) belongs to tile t.  The table is the transpose of eight ctx masks, built
+// four tiles at a time: nibble * 0x00204081 puts bit j of the nibble at bit 8j (terms at offsets 0,7,14,21 never
+// overlap), shifted by k for mask k.
+#define QZ_TILE_TABLE_WORDS 21
+QZ_HD uint32_t qz_tile_group(uint32_t n, uint32_t s, uint32_t e, uint32_t w, uint32_t a, uint32_t b, uint32_t c,
+                             uint32_t d, int sh) {
+#define QZ_SPREAD4(x, k) (((((x) >> sh) & 0xFu) * (0x00204081u << (k))) & (0x01010101u << (k)))
+    return QZ_SPREAD4(n, 0) | QZ_SPREAD4(s, 1) | QZ_SPREAD4(e, 2) | QZ_SPREAD4(w, 3) | QZ_SPREAD4(a, 4) |
+           QZ_SPREAD4(b, 5) | QZ_SPREAD4(c, 6) | QZ_SPREAD4(d, 7);
+#undef QZ_SPREAD4
+}
+// tbl may be any word-addressable memory with element stride `stride` (shared memory on the device)
+QZ_HD void qz_tile_table(const QzPawnCtx &c, uint32_t *tbl, int stride) {
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+        tbl[g * stride] = qz_tile_group(c.d.n.w0, c.d.s.w0, c.d.e.w0, c.d.w.w0, c.neV.w0, c.nwV.w0, c.seV.w0, c.swV.w0, 4 * g);
+#pragma unroll
+    for (int g = 0; g < 8; g++)
+        tbl[(8 + g) * stride] = qz_tile_group(c.d.n.w1, c.d.s.w1, c.d.e.w1, c.d.w.w1, c.neV.w1, c.nwV.w1, c.seV.w1, c.swV.w1, 4 * g);
+#pragma unroll
+    for (int g = 0; g < 5; g++)
+        tbl[(16 + g) * stride] = qz_tile_group(c.d.n.w2, c.d.s.w2, c.d.e.w2, c.d.w.w2, c.neV.w2, c.nwV.w2, c.seV.w2, c.swV.w2, 4 * g);
+}
+
+// Which plain move of the mover on L runs into the opponent on O with no wall between (one-hot N,S,E,W or 0):
+// the only case in which jump moves exist (quoridor.py:303,317,331,343).  Adjacency is by raw tile offset (:278-281).
+QZ_HD uint32_t qz_pawn_contact(uint32_t iL, int L, int O) {
+    const int d = O - L;
+    const uint32_t adj = (d == 9 ? 1u : 0u) | (d == -9 ? 2u : 0u) | (d == 1 ? 4u : 0u) | (d == -1 ? 8u : 0u);
+    return iL & adj;
+}
+// quoridor.py:272-353 from info bytes: iL / iO of the mover's and the opponent's tile, hO = "corner is a
+// HORIZONTAL wall" bits of the opponent's tile (bit 0 NE, 1 NW, 2 SE, 3 SW; only read on east / west contact).
+// Same result as qz_pawn_moves_ctx for L, O on the board.
+QZ_HD uint32_t qz_pawn_moves_info(uint32_t iL, uint32_t iO, uint32_t hO, int L, int O, int player) {
+    const int d = O - L;
+    const uint32_t adj = (d == 9 ? 1u : 0u) | (d == -9 ? 2u : 0u) | (d == 1 ? 4u : 0u) | (d == -1 ? 8u : 0u);
+    uint32_t m = iL & 0xFu & ~adj;
+    if (player == 1 && L >= 72) m |= 1u;                       // :295
+    if (player == 2 && L < 9) m |= 2u;                         // :296-297
+    const uint32_t g = iL & adj;
+    if (g) {
+        const uint32_t nV = ~(iL | iO);                        // bit 4..7: corner is vertical on neither tile
+        if (g & 1u) {
+            const uint32_t nn = (iO & 1u) | ((player == 1 && L >= 63) ? 1u : 0u);              // :305-308
+            m |= (nn << 4) | (((nV >> 4) & 1u) << 8) | (((nV >> 5) & 1u) << 9);                 // :310-314
+        } else if (g & 2u) {
+            const uint32_t ss = ((iO >> 1) & 1u) | ((player == 2 && L < 18) ? 1u : 0u);        // :319-321
+            m |= (ss << 5) | (((nV >> 6) & 1u) << 10) | (((nV >> 7) & 1u) << 11);               // :323-327
+        } else if (g & 4u) {
+            m |= (((iO >> 2) & 1u) << 6) | (((~hO) & 1u) << 8) | (((~hO >> 2) & 1u) << 10);     // :333-339
+        } else {
+            m |= (((iO >> 3) & 1u) << 7) | (((~hO >> 1) & 1u) << 9) | (((~hO >> 3) & 1u) << 11); // :345-351
+        }
+    }
+    return m;
+}
+
 // ---- jump edges seen by the path check ------------------------------------------------------------------
 // In _bfs_to_goal (quoridor.py:479-528) the opponent pawn is a fixed obstacle: plain moves into its
 // tile are dropped and up to three jump edges leave each of the four neighbouring tiles.  Encoded as one

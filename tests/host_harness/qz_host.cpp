@@ -58,6 +58,16 @@ void qh_ctx_corners(uint64_t H, uint64_t V, unsigned char *out81, unsigned char 
     }
 }
 
+// pawn moves through the per-tile info table (the pawn-phase rollout kernel's path)
+unsigned qh_pawn_moves_info(uint64_t H, uint64_t V, int L, int O, int player) {
+    QzPawnCtx c = qz_ctx_build(H, V);
+    uint32_t tbl[QZ_TILE_TABLE_WORDS];
+    qz_tile_table(c, tbl, 1);
+    const unsigned char *b = reinterpret_cast<const unsigned char *>(tbl);
+    const uint32_t hO = bb_at(c.neH, O) | (bb_at(c.nwH, O) << 1) | (bb_at(c.seH, O) << 2) | (bb_at(c.swH, O) << 3);
+    return qz_pawn_moves_info(b[L], b[O], hO, L, O, player);
+}
+
 void qh_dirs_ctx(uint64_t H, uint64_t V, unsigned char *out81) {
     QzPawnCtx c = qz_ctx_build(H, V);
     for (int t = 0; t < 81; t++)

@@ -37,6 +37,9 @@ def qh():
     L.qh_legal_mask.argtypes = [u64p, u64p]
     L.qh_pawn_moves.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
     L.qh_pawn_moves.restype = C.c_uint
+    for fn in (L.qh_pawn_moves_ctx, L.qh_pawn_moves_info):
+        fn.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
+        fn.restype = C.c_uint
     L.qh_dirs.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p]
     L.qh_dirs_incremental.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_char_p]
     L.qh_spread8.argtypes = [C.c_uint64, C.POINTER(C.c_uint32)]
@@ -162,13 +165,14 @@ def test_corner_masks_match_scalar_corners(qh):
 
 
 def test_pawn_moves_golden(qh, pawn_cases):
-    qh.qh_pawn_moves_ctx.argtypes = [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int]
-    qh.qh_pawn_moves_ctx.restype = C.c_uint
     for H, V, loc, opp, player, want in pawn_cases:
         got = qh.qh_pawn_moves(H, V, loc, opp, player)
         assert [a for a in range(12) if got >> a & 1] == want
         got = qh.qh_pawn_moves_ctx(H, V, loc, opp, player)
         assert [a for a in range(12) if got >> a & 1] == want
+        if 0 <= opp <= 80:
+            got = qh.qh_pawn_moves_info(H, V, loc, opp, player)
+            assert [a for a in range(12) if got >> a & 1] == want
 
 
 def test_pawn_moves_vs_oracle_exhaustive_adjacency(qh):
@@ -185,6 +189,8 @@ def test_pawn_moves_vs_oracle_exhaustive_adjacency(qh):
                     got = qh.qh_pawn_moves(H, V, L, Op, player)
                     assert [a for a in range(12) if got >> a & 1] == want
                     got = qh.qh_pawn_moves_ctx(H, V, L, Op, player)
+                    assert [a for a in range(12) if got >> a & 1] == want
+                    got = qh.qh_pawn_moves_info(H, V, L, Op, player)
                     assert [a for a in range(12) if got >> a & 1] == want
 
 
