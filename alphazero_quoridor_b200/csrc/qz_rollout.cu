@@ -212,16 +212,22 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
     const uint8_t *my_tile = reinterpret_cast<const uint8_t *>(sm.tile + tid * QZ_TILE_TABLE_WORDS);
     unsigned long long *work = a.list_mode ? a.counter + 5 : a.counter + 2;
     const int64_t total = a.list_mode ? (int64_t)a.counter[3] : a.n_rollouts;
-    QzRng rng = qz_rng_init(0, 0);
+    // Philox blocks: `cur` serves plies 4q..4q+3, `nxt` is block q+1.  Lanes cross block boundaries on different
+    // iterations, so computing a block on demand would run the 10 rounds with a quarter of the lanes on almost
+    // every iteration; instead every busy lane refreshes `nxt` on every fourth iteration of the (warp-uniform)
+    // loop -- a lane plays one ply per iteration, hence crosses exactly one boundary in between.
+    QzPhilox4 cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
+    uint64_t rid = 0;
     int64_t r = -1;
     int L = 0, O = 0, mover = 1, steps = 0, steps0 = 0, player0 = 0;
     uint32_t iL = 0, iO = 0;
     unsigned long long my_plies = 0;
     bool exhausted = false;
-    for (;;) {
+    for (unsigned iter = 0;; iter++) {
         const bool want = (r < 0) && !exhausted;
         const unsigned want_lanes = __ballot_sync(QZ_FULL_MASK, want);
         const unsigned busy_lanes = __ballot_sync(QZ_FULL_MASK, r >= 0);
+        if ((iter & 3u) == 0 && r >= 0) nxt = qz_philox(a.seed, rid, ((uint32_t)steps >> 2) + 1u, 0);
         if (want_lanes && (busy_lanes == 0 || __popc(want_lanes) >= QZ_PAWN_REFILL)) {
             // claim until every wanting lane holds a LIVE pawn-phase rollout (or the work is gone); rollouts that
             // already ended in the wall phase, or are parked for the stuck kernel, are settled on the spot
@@ -255,9 +261,11 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
                 O = mover == 1 ? qz_p2(s.meta) : qz_p1(s.meta);
                 steps = steps0 = st;
                 player0 = qz_cur(m0);
-                rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + got) : a.rid_base + (uint64_t)got);
+                rid = a.rids ? __ldg(a.rids + got) : a.rid_base + (uint64_t)got;
             }
             if (fresh) {
+                cur = qz_philox(a.seed, rid, (uint32_t)steps >> 2, 0);
+                nxt = qz_philox(a.seed, rid, ((uint32_t)steps >> 2) + 1u, 0);
                 const QzPawnCtx c = qz_ctx_build(H, V);
                 qz_tile_table(c, sm.tile + tid * QZ_TILE_TABLE_WORDS, 1);
                 uint32_t *hm = sm.hmask + tid;
@@ -289,10 +297,15 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
                 add_flags = QZ_FLAG_STALEMATE;
                 finished = true;
             } else {
-                const uint32_t word = qz_rng_first_word(rng, (uint32_t)steps);
-                for (int k = (int)__umulhi(word, (uint32_t)np); k > 0; k--) pm &= pm - 1;      // drop the k lowest moves
-                L += sm.delta[__ffs(pm) - 1];                                                   // quoridor.py:217-243
+                const uint32_t word = qz_philox_word(cur, steps & 3);           // attempt 0 of ply `steps` (qz_sample.cuh)
+                int k = (int)__umulhi(word, (uint32_t)np);                       // drop the k lowest moves
+                if (k > 0) pm &= pm - 1;
+                if (k > 1) pm &= pm - 1;
+                if (k > 2) pm &= pm - 1;
+                for (k -= 3; k > 0; k--) pm &= pm - 1;
+                L += sm.delta[__ffs(pm) - 1];                                    // quoridor.py:217-243
                 steps++;
+                if ((steps & 3) == 0) cur = nxt;
                 if (mover == 1 ? L > 71 : L < 9) {            // :193-202; the mover is not rotated on a win (:176-181)
                     winner = mover;
                     add_flags = QZ_FLAG_DONE | ((unsigned)winner << QZ_FLAG_WINNER_SHIFT);

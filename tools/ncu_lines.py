@@ -55,10 +55,16 @@ def main():
     attr_file = sys.argv[3] if len(sys.argv) > 3 else None
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
-    hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
+    # the report may hold several kernels: take the first section whose kernel name matches
+    start = next(i for i, r in enumerate(rows) if len(r) > 1 and r[0] == "Kernel Name" and kern in r[1])
+    hdr = next(i for i in range(start, len(rows)) if rows[i] and rows[i][0] == "Address")
     h = rows[hdr]
     ia, ii, it = h.index("Address"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
-    insts = [(int(r[ia], 16), int(r[ii]), int(r[it])) for r in rows[hdr + 1:] if len(r) == len(h)]
+    insts = []
+    for r in rows[hdr + 1:]:
+        if len(r) != len(h) or r[0] in ("Address", "Kernel Name"):
+            break
+        insts.append((int(r[ia], 16), int(r[ii]), int(r[it])))
     base = insts[0][0]
     table = {off: (txt, fr) for off, txt, fr in line_table(kern)}
     agg, tot, ttot = {}, 0, 0
