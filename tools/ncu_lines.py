@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Per-source-line instruction counts of one profiled kernel.
 
-  python tools/ncu_lines.py REPORT.ncu-rep KERNEL_SUBSTR [FILE_TO_ATTRIBUTE_TO]
+  python tools/ncu_lines.py REPORT.ncu-rep KERNEL_SUBSTR [FILE_TO_ATTRIBUTE_TO [inner]]
 
 Joins `ncu --page source --csv` (SASS view: executed instructions per SASS instruction) with
 `nvdisasm -gi` of the cubin embedded in libqzb200.so (file:line + inlined-at chain per instruction), and prints
@@ -53,6 +53,7 @@ def line_table(kernel_substr):
 def main():
     rep, kern = sys.argv[1], sys.argv[2]
     attr_file = sys.argv[3] if len(sys.argv) > 3 else None
+    inner = len(sys.argv) > 4 and sys.argv[4] == "inner"       # innermost frame inside FILE instead of outermost
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(out.splitlines()))
     # the report may hold several kernels: take the first section whose kernel name matches
@@ -77,6 +78,8 @@ def main():
                 for f in fr:                      # innermost first; keep the outermost frame inside attr_file
                     if f[0] == attr_file:
                         key = f
+                        if inner:
+                            break
         a = agg.setdefault(key, [0, 0])
         a[0] += n
         a[1] += tn
