@@ -37,6 +37,7 @@ SIGNATURES = {
     "qz_env_sample_legal": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _i64, _vp]),
     "qz_env_random_play": (C.c_int, [_vp, _u64, _vp, _i32, _i64, _vp]),
     "qz_rollout_workspace_bytes": (C.c_int64, [_i64]),
+    "qz_rollout_pawn_passes": (C.c_int32, [C.c_int32]),
     "qz_rollout": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _vp]),
     "qz_rollout_finish": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "qz_mcts_backup_pending": (C.c_int, [_vp, _vp, C.c_int, _vp]),
@@ -76,14 +77,14 @@ def load():
 LAUNCHES = 0      # kernels of ours launched through the C ABI (bench.py reports it as gpu_launches)
 
 
-# kernels launched by one successful call of each entry point (qz_rollout: wall + stuck + pawn, one fewer when the
-# stuck pass is deferred -- counted as 3 here and 2 for qz_rollout_finish, so a deferred pair is over- by one)
-KERNELS_PER_CALL = {"qz_rollout": 3, "qz_rollout_finish": 2, "qz_env_random_play": 2}
+# kernels launched by one successful call of each entry point; the rollout entry points pass their own count
+# (wall + stuck + qz_rollout_pawn_passes(limit) pawn passes, see rollout.py)
+KERNELS_PER_CALL = {"qz_env_random_play": 2}
 
 
-def check(rc, what=""):
+def check(rc, what="", launches=None):
     global LAUNCHES
-    LAUNCHES += KERNELS_PER_CALL.get(what, 1)
+    LAUNCHES += KERNELS_PER_CALL.get(what, 1) if launches is None else launches
     if rc != 0:
         msg = load().qz_last_error_string().decode("utf-8", "replace")
         raise QzError("%s failed with code %d: %s" % (what or "libqzb200 call", rc, msg))

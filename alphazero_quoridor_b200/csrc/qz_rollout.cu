@@ -26,12 +26,18 @@ struct QzRolloutArgs {
     int8_t *result;                // [n_rollouts] +1/-1/0 from the starting mover's view
     int32_t *plies;                // nullable [n_rollouts]
     qz_state *final_states;        // nullable [n_rollouts]
-    unsigned long long *counter;   // [0] wall-phase work counter, [1] cumulative plies, [2] pawn-phase work counter,
-                                   // [3] number of ejected ("stuck") rollouts, [4] stuck-phase work counter,
-                                   // [5] pawn-phase work counter of the deferred pass
-    int32_t list_mode;             // pawn kernel: 0 = all rollouts, 1 = only those of stuck_list (deferred pass)
-    qz_state *mid;                 // [n_rollouts] state when a rollout leaves a phase
+    unsigned long long *counter;   // workspace header, QZ_WS_COUNTERS words: [0] wall-phase work counter, [1] cumulative
+                                   // plies (never zeroed), [3] number of ejected ("stuck") rollouts, [4] stuck-phase work
+                                   // counter, [8 + 2j] work counter of pawn pass j, [9 + 2j] rollouts surviving pass j
+    qz_state *mid;                 // [n_rollouts] state when a rollout leaves a phase / is suspended
     int32_t *stuck_list;           // [n_rollouts] rollouts ejected from the wall phase
+    // one pawn-phase pass (set by qz_pawn_passes)
+    const int32_t *list_in;        // nullable: the rollouts of this pass (else all of them)
+    const unsigned long long *count_in;   // nullable: how many (else n_rollouts)
+    int32_t *list_out;             // rollouts suspended by this pass, *count_out of them
+    unsigned long long *count_out;
+    unsigned long long *work;      // work counter of this pass
+    int32_t slice;                 // plies a rollout may play per pass
 };
 
 // Warp-aggregated claim of the next unstarted rollout for every idle lane; returns -1 when none is left.
@@ -210,8 +216,7 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
     if (tid < 12) sm.delta[tid] = qz_delta(tid);
     __syncthreads();
     const uint8_t *my_tile = reinterpret_cast<const uint8_t *>(sm.tile + tid * QZ_TILE_TABLE_WORDS);
-    unsigned long long *work = a.list_mode ? a.counter + 5 : a.counter + 2;
-    const int64_t total = a.list_mode ? (int64_t)a.counter[3] : a.n_rollouts;
+    const int64_t total = a.count_in ? (int64_t)*a.count_in : a.n_rollouts;
     // Philox blocks: `cur` serves plies 4q..4q+3, `nxt` is block q+1.  Lanes cross block boundaries on different
     // iterations, so computing a block on demand would run the 10 rounds with a quarter of the lanes on almost
     // every iteration; instead every busy lane refreshes `nxt` on every fourth iteration of the (warp-uniform)
@@ -219,7 +224,7 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
     QzPhilox4 cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
     uint64_t rid = 0;
     int64_t r = -1;
-    int L = 0, O = 0, mover = 1, steps = 0, steps0 = 0, player0 = 0;
+    int L = 0, O = 0, mover = 1, steps = 0, steps0 = 0, player0 = 0, left = 0;
     uint32_t iL = 0, iO = 0;
     unsigned long long my_plies = 0;
     bool exhausted = false;
@@ -234,9 +239,9 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
             bool need = want, fresh = false;
             uint64_t H = 0, V = 0;
             while (__any_sync(QZ_FULL_MASK, need)) {
-                int64_t got = qz_claim(work, need, total);
+                int64_t got = qz_claim(a.work, need, total);
                 if (!need) continue;
-                if (got >= 0 && a.list_mode) got = a.stuck_list[got];
+                if (got >= 0 && a.list_in) got = a.list_in[got];
                 if (got < 0) { exhausted = true; need = false; continue; }
                 const QzState s = qz_load_state(a.mid + got);
                 const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, got)) + 2);
@@ -260,6 +265,7 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
                 L = mover == 1 ? qz_p1(s.meta) : qz_p2(s.meta);
                 O = mover == 1 ? qz_p2(s.meta) : qz_p1(s.meta);
                 steps = steps0 = st;
+                left = a.slice;
                 player0 = qz_cur(m0);
                 rid = a.rids ? __ldg(a.rids + got) : a.rid_base + (uint64_t)got;
             }
@@ -316,9 +322,20 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
                     iL = iO; iO = moved;
                     mover = 3 - mover;
                     finished = steps >= a.limit - 1;
+                    if (!finished && --left == 0) {
+                        // end of this pass's slice: park the rollout; the next pass resumes it among the other survivors,
+                        // packed into full warps again (only the meta word changes in the pawn phase)
+                        uint64_t *mw = reinterpret_cast<uint64_t *>(a.mid + r) + 2;
+                        const uint64_t m = *mw;
+                        const unsigned ply = qz_ply(m) + (unsigned)(steps - steps0);
+                        *mw = qz_pack_meta(mover == 1 ? L : O, mover == 1 ? O : L, 0, 0, mover, qz_flags(m),
+                                           ply < 0xFFFFu ? ply : 0xFFFFu);
+                        a.list_out[atomicAdd(a.count_out, 1ull)] = (int32_t)r;
+                        r = -1;
+                    }
                 }
             }
-            if (finished) {
+            if (finished && r >= 0) {
                 a.result[r] = qz_pawn_result(winner, player0);
                 if (a.plies) a.plies[r] = steps;
                 if (a.final_states) {
@@ -339,9 +356,16 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
     if ((tid & 31) == 0 && my_plies) atomicAdd(a.counter + 1, my_plies);
 }
 
+// workspace: header | mid[n] | stuck_list[n] | two survivor lists [n] (ping-pong between pawn passes)
+#define QZ_WS_COUNTERS 64
+#define QZ_WS_HEADER_BYTES (QZ_WS_COUNTERS * 8)
+#define QZ_PAWN_SLICE 128
+#define QZ_PAWN_MAX_PASSES ((QZ_WS_COUNTERS - 8) / 2)
+static int64_t qz_list_bytes(int64_t n) { return ((n * 4 + 7) / 8) * 8; }
+
 extern "C" int64_t qz_rollout_workspace_bytes(int64_t n_rollouts) {
     const int64_t n = n_rollouts > 0 ? n_rollouts : 0;
-    return 64 + n * (int64_t)sizeof(qz_state) + ((n * 4 + 7) / 8) * 8;
+    return QZ_WS_HEADER_BYTES + n * (int64_t)sizeof(qz_state) + 3 * qz_list_bytes(n);
 }
 
 static int qz_persistent_blocks(const void *kernel, int64_t n_items, int items_per_block, int threads = 128) {
@@ -353,6 +377,50 @@ static int qz_persistent_blocks(const void *kernel, int64_t n_items, int items_p
     int64_t blocks = (int64_t)sms * per_sm;                 // one resident wave: a multiple of the SM count
     const int64_t needed = (n_items + items_per_block - 1) / items_per_block;
     return (int)(blocks < needed ? blocks : needed);
+}
+
+// The pawn phase as a sequence of passes.  A rollout plays at most `slice` plies per pass and is then parked; the next
+// pass picks the survivors up from a list, so they sit in full warps again instead of keeping a few lanes of
+// every warp alive for up to `limit` iterations (rollout lengths are heavy-tailed: mean ~300 plies, cap 1000).
+// The number of survivors is only known on the device: every pass launches a resident grid whose blocks exit at
+// once when there is nothing to claim.  `finish` = the deferred pass over stuck_list.
+static int64_t qz_pawn_slice(int64_t limit, int *passes) {
+    const int64_t span = limit > 1 ? limit - 1 : 1;                     // a rollout never plays more plies than this
+    int64_t slice = QZ_PAWN_SLICE;
+    if ((span + slice - 1) / slice > QZ_PAWN_MAX_PASSES) slice = (span + QZ_PAWN_MAX_PASSES - 1) / QZ_PAWN_MAX_PASSES;
+    *passes = (int)((span + slice - 1) / slice);
+    return slice;
+}
+
+extern "C" int32_t qz_rollout_pawn_passes(int32_t limit) {
+    int passes = 0;
+    qz_pawn_slice(limit, &passes);
+    return passes;
+}
+
+static int qz_pawn_passes(QzRolloutArgs a, bool finish, cudaStream_t st, const char *what) {
+    int passes = 0;
+    const int64_t slice = qz_pawn_slice(a.limit, &passes);
+    int32_t *lists[2] = {a.stuck_list + qz_list_bytes(a.n_rollouts) / 4, a.stuck_list + 2 * (qz_list_bytes(a.n_rollouts) / 4)};
+    int blocks = qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, a.n_rollouts, QZ_PAWN_THREADS);
+    if (finish) blocks = blocks / 4 > 0 ? blocks / 4 : 1;              // the deferred list is well under 1 % of the rollouts
+    a.slice = (int32_t)slice;
+    for (int j = 0; j < passes; j++) {
+        a.work = a.counter + 8 + 2 * j;
+        a.count_out = a.counter + 9 + 2 * j;
+        a.list_out = lists[j & 1];
+        if (j == 0) {
+            a.list_in = finish ? a.stuck_list : nullptr;
+            a.count_in = finish ? a.counter + 3 : nullptr;
+        } else {
+            a.list_in = lists[(j - 1) & 1];
+            a.count_in = a.counter + 9 + 2 * (j - 1);
+        }
+        qz_rollout_pawn_kernel<<<blocks, QZ_PAWN_THREADS, 0, st>>>(a);
+        const int rc = qz_check_launch(what);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 static int qz_rollout_args(QzRolloutArgs &a, const qz_state *states, int64_t n_states, const int32_t *state_index,
@@ -370,9 +438,9 @@ static int qz_rollout_args(QzRolloutArgs &a, const qz_state *states, int64_t n_s
     a.n_rollouts = n_rollouts; a.per_state = per_state > 0 ? per_state : 1; a.limit = limit;
     a.result = result; a.plies = plies; a.final_states = final_states;
     a.counter = (unsigned long long *)workspace;
-    a.list_mode = 0;
-    a.mid = (qz_state *)((char *)workspace + 64);
-    a.stuck_list = (int32_t *)((char *)workspace + 64 + n_rollouts * (int64_t)sizeof(qz_state));
+    a.mid = (qz_state *)((char *)workspace + QZ_WS_HEADER_BYTES);
+    a.stuck_list = (int32_t *)((char *)workspace + QZ_WS_HEADER_BYTES + n_rollouts * (int64_t)sizeof(qz_state));
+    a.list_in = nullptr; a.count_in = nullptr; a.list_out = nullptr; a.count_out = nullptr; a.work = nullptr; a.slice = 0;
     return 0;
 }
 
@@ -386,7 +454,7 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
     if (rc || n_rollouts == 0) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(a.counter, 0, 8, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(a.counter + 2, 0, 32, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.counter + 2, 0, (QZ_WS_COUNTERS - 2) * 8, st);
     if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout: memset: %s", cudaGetErrorString(e));
     qz_rollout_wall_kernel<<<qz_persistent_blocks((const void *)qz_rollout_wall_kernel, n_rollouts, 128), 128, 0, st>>>(a);
     rc = qz_check_launch("qz_rollout (wall phase)");
@@ -397,9 +465,7 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
         rc = qz_check_launch("qz_rollout (stuck phase)");
         if (rc) return rc;
     }
-    qz_rollout_pawn_kernel<<<qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, QZ_PAWN_THREADS),
-                             QZ_PAWN_THREADS, 0, st>>>(a);
-    return qz_check_launch("qz_rollout (pawn phase)");
+    return qz_pawn_passes(a, false, st, "qz_rollout (pawn phase)");
 }
 
 // The deferred pass of qz_rollout(..., QZ_ROLLOUT_DEFER_STUCK): same arguments and buffers.
@@ -411,14 +477,11 @@ extern "C" int qz_rollout_finish(const qz_state *states, int64_t n_states, const
                              plies, final_states, workspace, "qz_rollout_finish");
     if (rc || n_rollouts == 0) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t e = cudaMemsetAsync(a.counter + 4, 0, 16, st);
+    cudaError_t e = cudaMemsetAsync(a.counter + 4, 0, 8, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(a.counter + 8, 0, (QZ_WS_COUNTERS - 8) * 8, st);
     if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout_finish: memset: %s", cudaGetErrorString(e));
     qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 4, 128), 128, 0, st>>>(a);
     rc = qz_check_launch("qz_rollout_finish (stuck phase)");
     if (rc) return rc;
-    a.list_mode = 1;
-    // the deferred list is short (well under 1 % of the rollouts): a quarter of a resident wave is plenty
-    int blocks = qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, n_rollouts, QZ_PAWN_THREADS) / 4;
-    qz_rollout_pawn_kernel<<<blocks > 0 ? blocks : 1, QZ_PAWN_THREADS, 0, st>>>(a);
-    return qz_check_launch("qz_rollout_finish (pawn phase)");
+    return qz_pawn_passes(a, true, st, "qz_rollout_finish (pawn phase)");
 }

@@ -54,9 +54,11 @@ def rollout(states, per_state=1, seed=0, rid_base=0, rids=None, state_index=None
     args = [_lib.ptr(states), n_states, _lib.ptr(state_index), int(per_state), n_roll, int(seed) & ((1 << 64) - 1),
             int(rid_base) & ((1 << 64) - 1), _lib.ptr(rids), int(limit), _lib.ptr(result), _lib.ptr(plies),
             _lib.ptr(final), _lib.ptr(workspace)]
+    passes = lib.qz_rollout_pawn_passes(int(limit))
     with torch.cuda.device(dev):
-        if finish:
-            _lib.check(lib.qz_rollout_finish(*args, _lib.stream_ptr(dev)), "qz_rollout_finish")
-        else:
-            _lib.check(lib.qz_rollout(*args, DEFER_STUCK if defer_stuck else 0, _lib.stream_ptr(dev)), "qz_rollout")
+        if finish:       # stuck kernel + pawn passes
+            _lib.check(lib.qz_rollout_finish(*args, _lib.stream_ptr(dev)), "qz_rollout_finish", launches=1 + passes)
+        else:            # wall kernel (+ stuck kernel unless deferred) + pawn passes
+            _lib.check(lib.qz_rollout(*args, DEFER_STUCK if defer_stuck else 0, _lib.stream_ptr(dev)), "qz_rollout",
+                       launches=(1 if defer_stuck else 2) + passes)
     return result, plies, final

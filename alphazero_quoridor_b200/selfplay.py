@@ -17,7 +17,7 @@ from .tree import BatchedMCTS, RolloutEvaluator
 class BatchedSelfPlay:
     def __init__(self, n_games, evaluator, c_puct=5, n_playout=400, leaves_per_game=8, temp=1.0, pure=False,
                  seed=0, game_id_base=0, max_plies=600, record=False, fix_terminal_sign=False, device=None,
-                 node_cap=None, defer_depth=0):
+                 node_cap=None, defer_depth=0, defer_until_drain=False):
         self.pure = bool(pure)
         self.temp = float(temp)
         self.seed = int(seed)
@@ -26,7 +26,7 @@ class BatchedSelfPlay:
         self.mcts = BatchedMCTS(n_games, evaluator, c_puct=c_puct, n_playout=n_playout,
                                 leaves_per_game=leaves_per_game, reuse_tree=not self.pure,
                                 fix_terminal_sign=fix_terminal_sign, device=device, node_cap=node_cap,
-                                defer_depth=defer_depth)
+                                defer_depth=defer_depth, defer_until_drain=defer_until_drain)
         self.n = self.mcts.n
         dev = self.device = self.mcts.device
         self.lib = self.mcts.lib

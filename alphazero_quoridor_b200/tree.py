@@ -146,7 +146,8 @@ class NetEvaluator:
 # ------------------------------------------------------------------------------------------------ the search
 class BatchedMCTS:
     def __init__(self, n_games, evaluator, c_puct=5, n_playout=100, leaves_per_game=1, node_cap=None,
-                 max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None, defer_depth=0):
+                 max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None, defer_depth=0,
+                 defer_until_drain=False):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda")
@@ -171,7 +172,14 @@ class BatchedMCTS:
         m = self.n * self.K
         # deferred evaluation (stuck rollouts finished on a side stream while later waves run): wave w's owed
         # backups are applied just before wave w + defer_depth reuses its leaf set
+        # defer_until_drain: the deferred passes of ALL waves of a search are launched together when the search
+        # drains (before statistics are read / a move is chosen): thousands of stuck rollouts at once fill the SMs,
+        # where one wave's few hundred are a latency-bound trickle that crowds the next waves' kernels
+        # (profiles/README.md r1m); needs one leaf set per wave of a search.
         self.defer_depth = int(defer_depth) if getattr(evaluator, "can_defer", False) else 0
+        self.defer_until_drain = bool(defer_until_drain) and getattr(evaluator, "can_defer", False)
+        if self.defer_until_drain:
+            self.defer_depth = max(self.defer_depth, 2 + (self.n_playout + self.K - 1) // self.K)
         self.sets = [_LeafSet(m, self.max_depth, dev) for _ in range(max(1, self.defer_depth))]
         self.cur_set = 0
         self.wave_index = 0
@@ -250,11 +258,24 @@ class BatchedMCTS:
                                              self._stream()), "qz_mcts_init")
         self.playouts_done = 0
 
+    def _launch_finish(self, idx):
+        """Start the deferred pass of wave (self.sets[idx]) on that set's side stream."""
+        ls = self.sets[idx]
+        cur = torch.cuda.current_stream(self.device)
+        side = self.side_streams[idx]
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            ls.owed["result"] = self.evaluator.finish(self, ls)
+            ls.owed["done"] = torch.cuda.Event()
+            ls.owed["done"].record()
+
     def _settle(self, idx):
         """Apply the backups wave (self.sets[idx]) still owes: wait for its deferred rollouts, then back them up."""
         ls = self.sets[idx]
         if ls.owed is None:
             return
+        if "done" not in ls.owed:
+            self._launch_finish(idx)
         torch.cuda.current_stream(self.device).wait_event(ls.owed["done"])
         _lib.check(self.lib.qz_mcts_backup_pending(C.byref(self._structs[self.cur][idx]), _lib.ptr(ls.owed["result"]),
                                                    int(self.fix_terminal_sign), self._stream()), "qz_mcts_backup_pending")
@@ -264,8 +285,12 @@ class BatchedMCTS:
         """Settle every deferred wave (before reading statistics, choosing a move or re-rooting)."""
         if self.defer_depth >= 2:
             with torch.cuda.device(self.device):
-                for i in range(len(self.sets)):
-                    self._settle((self.cur_set + 1 + i) % len(self.sets))      # oldest first
+                order = [(self.cur_set + 1 + i) % len(self.sets) for i in range(len(self.sets))]     # oldest first
+                for idx in order:                      # start every pass that is still to run, then collect them
+                    if self.sets[idx].owed is not None and "done" not in self.sets[idx].owed:
+                        self._launch_finish(idx)
+                for idx in order:
+                    self._settle(idx)
 
     def playout_wave(self, k_leaves=None):
         """One wave: k_leaves playouts per game (mcts.py:103-127)."""
@@ -293,15 +318,9 @@ class BatchedMCTS:
                 C.byref(self.tree), _lib.ptr(ls.leaf_mask), _lib.ptr(ev.get("priors")),
                 _lib.ptr(ev.get("value_f32")), _lib.ptr(ev.get("value_f64")), _lib.ptr(ev.get("value_i8")),
                 int(self.fix_terminal_sign), _lib.ptr(self.overflow), st), "qz_mcts_expand_backup")
-            if defer:
+            if defer and not self.defer_until_drain:
                 # finish the stuck rollouts of this wave on the side stream while the next waves run
-                cur = torch.cuda.current_stream(self.device)
-                side = self.side_streams[self.cur_set]
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    ls.owed["result"] = self.evaluator.finish(self, ls)
-                    ls.owed["done"] = torch.cuda.Event()
-                    ls.owed["done"].record()
+                self._launch_finish(self.cur_set)
         self.playouts_done += k
         self.total_playouts += k
         self.wave_index += 1

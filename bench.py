@@ -23,6 +23,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the end-of-search pass runs ~18 stuck-rollout kernels on as many streams: with the default 8 hardware queues they
+# would serialise in three rounds (must be set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 METRIC = "env_steps_per_s"
 UNIT = "env steps/s"
@@ -37,8 +40,9 @@ def parse():
     ap.add_argument("--games", type=int, default=4096, help="concurrent games per GPU")
     ap.add_argument("--playouts", type=int, default=1000)
     ap.add_argument("--leaves", type=int, default=64, help="leaves per game per wave (virtual loss)")
-    ap.add_argument("--streams", type=int, default=2, help="sub-batches of games on separate CUDA streams")
-    ap.add_argument("--defer", type=int, default=4, help="waves a stuck rollout may lag behind (0 = finish in-wave)")
+    ap.add_argument("--streams", type=int, default=1, help="sub-batches of games on separate CUDA streams")
+    ap.add_argument("--defer", type=int, default=-1,
+                    help="waves a stuck rollout may lag behind (0 = finish in-wave, -1 = all of them at the end of the search)")
     ap.add_argument("--c-puct", type=float, default=5.0)
     ap.add_argument("--seed", type=int, default=20261017)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -225,7 +229,8 @@ def run_ours(args):
 
     sp = StreamedSelfPlay(args.games, make_evaluator, n_streams=args.streams, c_puct=args.c_puct,
                           n_playout=args.playouts, leaves_per_game=args.leaves, pure=True, seed=args.seed,
-                          game_id_base=rank * args.games, device=dev, defer_depth=args.defer,
+                          game_id_base=rank * args.games, device=dev, defer_depth=max(args.defer, 0),
+                          defer_until_drain=args.defer < 0,
                           fix_terminal_sign=args.fix_terminal_sign)
     engines = [s.mcts for s in sp.subs]
     for m in engines:
@@ -367,7 +372,7 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(args), "games_per_gpu": args.games, "playouts_per_move": args.playouts,
                    "leaves_per_game_per_wave": args.leaves, "cuda_streams": args.streams,
-                   "stuck_rollout_defer_waves": args.defer, "fix_terminal_sign": bool(args.fix_terminal_sign),
+                   "stuck_rollout_defer_waves": args.defer if args.defer >= 0 else "end of search", "fix_terminal_sign": bool(args.fix_terminal_sign),
                    "parallelism": "games sharded by index x%d, no collective" % world,
                    "l2": "inputs larger than L2: tree arenas %.1f GB/GPU; rollouts are register resident"
                          % (sum(m.nbytes() for m in engines) / 1e9)},

@@ -138,11 +138,12 @@ int qz_env_encode(const qz_state *states, void *out, int dtype, int layout, int 
  *   limit                the reference's `limit` (1000): at most limit-1 plies are played.
  *   result[r]            +1 / -1 from the STARTING mover's point of view, 0 if nobody won (:104-108).
  *   plies[r]             (nullable) plies played.     final_states[r]  (nullable) where the rollout ended.
- *   workspace            qz_rollout_workspace_bytes(n_rollouts) bytes of device scratch (8-byte aligned).  64-bit
- *                        words 0, 2, 3, 4 are work / list counters (zeroed by the call); word 1 ACCUMULATES the
- *                        plies played by every call (caller zeroes / reads it), i.e. the env-step count without a
- *                        per-rollout reduction; from byte 64 on, one qz_state per rollout parks the position between
- *                        the phases (wall, stuck, pawn: three kernels), followed by the list of ejected rollouts.
+ *   workspace            qz_rollout_workspace_bytes(n_rollouts) bytes of device scratch (8-byte aligned).  The first
+ *                        64 64-bit words are work / list counters (zeroed by the call) except word 1, which
+ *                        ACCUMULATES the plies played by every call (caller zeroes / reads it), i.e. the env-step
+ *                        count without a per-rollout reduction; then one qz_state per rollout parks the position
+ *                        between the phases (wall kernel, stuck kernel, qz_rollout_pawn_passes(limit) pawn passes),
+ *                        the list of ejected rollouts and two lists of rollouts suspended between pawn passes.
  *   flags                QZ_ROLLOUT_DEFER_STUCK: the few rollouts ejected from the wall phase ("stuck": walls in hand
  *                        but next to no legal placement, hundreds of serial plies) are NOT finished by this call;
  *                        their result is QZ_ROLLOUT_PENDING (-128) until qz_rollout_finish, called later -- typically on
@@ -152,6 +153,9 @@ int qz_env_encode(const qz_state *states, void *out, int dtype, int layout, int 
 #define QZ_ROLLOUT_DEFER_STUCK 1
 #define QZ_ROLLOUT_PENDING (-128)
 int64_t qz_rollout_workspace_bytes(int64_t n_rollouts);
+/* kernel launches of the pawn phase of one qz_rollout / qz_rollout_finish call (a rollout plays a bounded slice
+ * of plies per pass, then the survivors are re-packed into full warps) */
+int32_t qz_rollout_pawn_passes(int32_t limit);
 int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
                int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
                int8_t *result, int32_t *plies, qz_state *final_states, void *workspace, int32_t flags, void *stream);

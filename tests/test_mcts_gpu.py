@@ -269,7 +269,8 @@ def test_sharding_invariance(qz):
 
 
 def test_deferred_stuck_rollouts(qz):
-    """defer_depth=3: the stuck rollouts of a wave finish on a side stream and are backed up three waves later.
+    """defer_depth=3: the stuck rollouts of a wave finish on a side stream and are backed up three waves later;
+    defer_until_drain: the stuck rollouts of every wave are finished together when the search ends.
     Nothing may be lost: every playout is counted once, no virtual loss is left behind, the run is deterministic
     and the chosen moves agree with the in-wave engine to the virtual-loss tolerance."""
     from alphazero_quoridor_b200.synthetic import midgame_positions
@@ -280,9 +281,9 @@ def test_deferred_stuck_rollouts(qz):
     sel = ((((meta >> 16) & 0xFF) + ((meta >> 24) & 0xFF)) > 0) & (((meta >> 40) & 1) == 0)
     states = torch.cat([pos[sel][:n // 2], midgame_positions(n, seed=6, min_plies=4, max_plies=30)], 0)[:n].contiguous()
     outs = []
-    for defer in (0, 3, 3):
+    for defer, at_drain in ((0, False), (3, False), (3, False), (0, True), (0, True)):
         eng = qz.tree.BatchedMCTS(n, qz.tree.RolloutEvaluator(seed=11), c_puct=5, n_playout=n_playout,
-                                  leaves_per_game=K, reuse_tree=False, defer_depth=defer)
+                                  leaves_per_game=K, reuse_tree=False, defer_depth=defer, defer_until_drain=at_drain)
         eng.game_id.copy_(torch.arange(n, dtype=torch.int64) << 32)
         eng.reset(states)
         eng.search()
@@ -298,11 +299,13 @@ def test_deferred_stuck_rollouts(qz):
             assert ((meta_nodes[g, :used[g]].astype(np.int64) & 0xFFFFFFFF) >> 16 == 0).all()    # no in-flight marks left
         outs.append((visits.cpu().numpy().astype(np.float64), eng.choose(mode=0).cpu().numpy()))
     assert np.array_equal(outs[1][0], outs[2][0]) and np.array_equal(outs[1][1], outs[2][1])     # deterministic
-    a, b = outs[0][0], outs[1][0]
+    assert np.array_equal(outs[3][0], outs[4][0]) and np.array_equal(outs[3][1], outs[4][1])     # deterministic
+    a = outs[0][0]
     ok = a.sum(1) > 0
-    tv = 0.5 * np.abs(a[ok] / a[ok].sum(1, keepdims=True) - b[ok] / b[ok].sum(1, keepdims=True)).sum(1)
-    print("deferred vs in-wave TV: mean %.4f" % tv.mean())
-    assert tv.mean() <= 0.15
+    for name, b in (("3 waves late", outs[1][0]), ("at the end of the search", outs[3][0])):
+        tv = 0.5 * np.abs(a[ok] / a[ok].sum(1, keepdims=True) - b[ok] / b[ok].sum(1, keepdims=True)).sum(1)
+        print("deferred (%s) vs in-wave TV: mean %.4f" % (name, tv.mean()))
+        assert tv.mean() <= 0.15
 
 
 def test_move_sampling_distributions(qz):
