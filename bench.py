@@ -346,7 +346,12 @@ def run_ours(args):
     avg_ms = avg_main + avg_stuck
     avg_n = sum(roll_n) / max(len(roll_n), 1)
     achieved = bytes_per_rollout * avg_n / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    roofline = {"kernel": "qz_rollout_wall_kernel + qz_rollout_pawn_kernel (main stream) + qz_rollout_stuck_kernel (side stream)",
+    # whole-step warp-instruction count from the committed launch list of this same command (profiles/r1m_bench_launches.txt:
+    # 398.54 G warp instructions over 7 steps of 4096 games x 1000 playouts), scaled to this run's playouts per step
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    issue_peak = sm_count * 4 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6           # warp instructions / s
+    inst_per_step = 398.54e9 / 7.0 * (args.games * args.playouts) / (4096.0 * 1000.0)
+    roofline = {"kernel": "qz_rollout_wall_kernel + qz_rollout_pawn_kernel passes (waves) + qz_rollout_stuck_kernel (end of search)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of the three kernels in profiles/r1g_rollout_ncu_full.txt
@@ -356,16 +361,27 @@ def run_ours(args):
                 "launches_timed": len(roll_ms), "avg_launch_ms": avg_ms, "avg_main_stream_ms": avg_main,
                 "avg_deferred_stuck_pass_ms": avg_stuck, "rollouts_per_launch": avg_n,
                 "share_of_step": (sum(roll_ms) + sum(stuck_ms)) / ms if ms > 0 else None,
-                "issue_profile": {"source": "profiles/r1e_rollout_ncu_full.txt, profiles/r1e_sweep_ncu_full.txt (ncu --set full, B200)",
-                                  "smsp_issue_active_pct": {"qz_rollout_wall_kernel": 60.9, "qz_rollout_pawn_kernel": 62.9,
-                                                            "qz_rollout_stuck_kernel": 37.6, "qz_legal_mask_kernel": 63.4},
-                                  "active_lanes_per_instruction": {"qz_rollout_wall_kernel": 18.6, "qz_rollout_pawn_kernel": 17.7,
-                                                                   "qz_rollout_stuck_kernel": 23.3, "qz_legal_mask_kernel": 21.3},
-                                  "note": "static numbers from the committed captures, not measured in this run"},
+                "issue_profile": {"source": "profiles/r1m_bench_launches.txt, profiles/r1m_rollout_ncu_full.txt, "
+                                            "profiles/r1m_sweep_ncu_full.txt (ncu, B200)",
+                                  "whole_step": {"warp_instructions": inst_per_step,
+                                                 "achieved_warp_inst_per_s": inst_per_step / (ms / args.steps * 1e-3) if ms > 0 else None,
+                                                 "peak_warp_inst_per_s": issue_peak,
+                                                 "frac": inst_per_step / (ms / args.steps * 1e-3) / issue_peak if ms > 0 else None,
+                                                 "note": "instruction count from the committed launch list (static), time from "
+                                                         "this run; the ALU-pipe-bound kernels below reach 0.60-0.76 alone"},
+                                  "instruction_share": {"qz_rollout_stuck_kernel": 0.296, "qz_legal_mask_kernel": 0.249,
+                                                        "qz_rollout_pawn_kernel": 0.188, "qz_rollout_wall_kernel": 0.119,
+                                                        "qz_mcts_select_kernel": 0.104, "qz_mcts_expand_backup_kernel": 0.044},
+                                  "smsp_issue_active_pct": {"qz_rollout_wall_kernel": 60.8, "qz_rollout_pawn_kernel (first pass)": 76.0,
+                                                            "qz_rollout_stuck_kernel": 43.3, "qz_legal_mask_kernel": 62.8},
+                                  "active_lanes_per_instruction": {"qz_rollout_wall_kernel": 18.6, "qz_rollout_pawn_kernel": 23.7,
+                                                                   "qz_rollout_stuck_kernel": 18.0, "qz_legal_mask_kernel": 18.7},
+                                  "note": "per-kernel numbers are static, from the committed captures"},
                 "note": "register-resident by design (24 B of state per game): instruction-issue / latency bound, not HBM "
-                        "bound (SURVEY.md 8d), so frac against the HBM peak is ~1e-5 and says nothing; the deferred stuck "
-                        "passes overlap later waves, so share_of_step sums concurrent streams and may exceed 1.  Warp-issue "
-                        "numbers are in profiles/; the HBM-bound kernels (step, encode) are under `kernels` with frac ~1."}
+                        "bound (SURVEY.md 8d), so frac against the HBM peak is ~1e-4 and says nothing -- issue_profile.whole_step "
+                        "is the meaningful fraction.  avg_deferred_stuck_pass_ms is the span of one of the ~17 concurrent "
+                        "end-of-search stuck passes, so share_of_step sums concurrent streams and exceeds 1.  The HBM-bound "
+                        "kernels (step, encode) are under `kernels` with frac ~1."}
     line = {
         "metric": METRIC, "value": env_total / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -1,5 +1,5 @@
 """Per-call durations with a device synchronize after every call (nothing overlaps): separates what a kernel costs
-from what concurrency does to it.  Usage: python tools/_serial_spans.py DEFER"""
+from what concurrency does to it.  Usage: python tools/serial_spans.py DEFER"""
 import sys, os, collections, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alphazero_quoridor_b200 import tree, _lib

@@ -1,5 +1,5 @@
 """Timeline of every C-ABI call of one pure-MCTS self-play step (CUDA events on the launching streams):
-start / end relative to the step start, per stream.  Usage: python tools/_wave_timeline.py STREAMS DEFER"""
+start / end relative to the step start, per stream.  Usage: python tools/wave_timeline.py STREAMS DEFER"""
 import sys, os, collections, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alphazero_quoridor_b200 import tree, _lib
