@@ -129,6 +129,9 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
 // a full sweep, and a rollout occupies one warp: the pass is latency-bound, so its throughput is the number of
 // rollouts resident per SM.
 
+#ifndef QZ_STUCK_THREADS
+#define QZ_STUCK_THREADS 32
+#endif
 __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
     const int lane = threadIdx.x & 31;
     for (;;) {
@@ -461,7 +464,8 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
     if (rc) return rc;
     if (!(flags & QZ_ROLLOUT_DEFER_STUCK)) {
         // the number of ejected rollouts is only known on the device: launch a resident grid, blocks exit when the list is empty
-        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 4, 128), 128, 0, st>>>(a);
+        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, QZ_STUCK_THREADS / 32, QZ_STUCK_THREADS),
+                                  QZ_STUCK_THREADS, 0, st>>>(a);
         rc = qz_check_launch("qz_rollout (stuck phase)");
         if (rc) return rc;
     }
@@ -480,7 +484,8 @@ extern "C" int qz_rollout_finish(const qz_state *states, int64_t n_states, const
     cudaError_t e = cudaMemsetAsync(a.counter + 4, 0, 8, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a.counter + 8, 0, (QZ_WS_COUNTERS - 8) * 8, st);
     if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout_finish: memset: %s", cudaGetErrorString(e));
-    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, 4, 128), 128, 0, st>>>(a);
+    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, QZ_STUCK_THREADS / 32, QZ_STUCK_THREADS),
+                                  QZ_STUCK_THREADS, 0, st>>>(a);
     rc = qz_check_launch("qz_rollout_finish (stuck phase)");
     if (rc) return rc;
     return qz_pawn_passes(a, true, st, "qz_rollout_finish (pawn phase)");
