@@ -121,6 +121,32 @@ def test_rollouts_vs_oracle(qz):
     assert set(np.unique(res)) <= {-1, 0, 1}
 
 
+@pytest.mark.parametrize("limit", [1, 2, 40, 129, 130, 258, 400, 5000])
+def test_rollout_limits_vs_oracle(qz, limit):
+    """pure_mcts.py:86-108 with other `limit`s: the pawn phase runs in 128-ply slices (one kernel pass each), so limits
+    around the slice boundaries, below one slice, and large enough to stretch the slices are checked ply for ply."""
+    from alphazero_quoridor_b200.rollout import rollout
+    from alphazero_quoridor_b200.synthetic import midgame_positions
+    from alphazero_quoridor_b200 import _lib
+    assert 1 <= _lib.load().qz_rollout_pawn_passes(limit) <= 28
+    late = midgame_positions(96, seed=21, min_plies=18, max_plies=44)         # some start inside the pawn phase
+    states = torch.cat([qz.BatchedQuoridor(32).states, late], 0).contiguous()
+    seed, base = 77 + limit, 31000
+    res, plies, final = rollout(states, per_state=2, seed=seed, rid_base=base, limit=limit, return_final=True)
+    res, plies = res.cpu().numpy(), plies.cpu().numpy()
+    fin = qz.BatchedQuoridor(final.shape[0], states=final).host_states()
+    src = qz.BatchedQuoridor(states.shape[0], states=states).host_states()
+    assert plies.max() <= max(limit - 1, 0)
+    for r in range(res.shape[0]):
+        d = src[r // 2]
+        g = O.OracleGame().set_position(d["H"], d["V"], d["p1"], d["p2"], d["w1"], d["w2"], d["cur"])
+        v, k = g.rollout(seed, base + r, limit)
+        pos, f = g.position(), fin[r]
+        assert (int(res[r]), int(plies[r])) == (v, k), (limit, r)
+        assert (f["H"], f["V"], f["p1"], f["p2"], f["w1"], f["w2"], f["cur"]) == (
+            pos["H"], pos["V"], pos["p1"], pos["p2"], pos["w1"], pos["w2"], pos["cur"]), (limit, r)
+
+
 def test_rollout_is_launch_shape_invariant(qz):
     """Outcome depends only on (state, seed, rid): explicit rids / state_index give the same answers."""
     from alphazero_quoridor_b200.rollout import rollout
