@@ -58,8 +58,9 @@ extern "C" int qz_mcts_init(const qz_tree *tree, const qz_state *root_states, co
 
 // ------------------------------------------------------------------------------------------ select
 // One warp per game; k_leaves sequential descents (virtual loss between them).
+#define QZ_SEL_MAX_CHILDREN 144        // a node has at most 140 children (12 pawn ids + 128 walls)
 template <bool UNIFORM_PRIOR>
-__global__ void __launch_bounds__(128) qz_mcts_select_kernel(qz_tree t, double c_puct, int k_leaves) {
+__global__ void __launch_bounds__(128, 7) qz_mcts_select_kernel(qz_tree t, double c_puct, int k_leaves) {
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= t.n_games) return;
     const int lane = threadIdx.x & 31;
@@ -72,6 +73,29 @@ __global__ void __launch_bounds__(128) qz_mcts_select_kernel(qz_tree t, double c
     const QzState root_state = qz_load_state(t.root_state + g);
     const int root = t.root[g];
     const int K = t.leaves_per_game;
+    // The k_leaves descents of a game all start at the root, whose children's statistics only change by the
+    // in-flight marks this warp sets itself: they are read once into shared memory, so the first level of every
+    // descent costs no global round trip (the select pass is a chain of dependent loads, ~4 per level).
+    __shared__ int32_t s_n[4][QZ_SEL_MAX_CHILDREN];
+    __shared__ uint32_t s_meta[4][QZ_SEL_MAX_CHILDREN];
+    __shared__ double s_q[4][QZ_SEL_MAX_CHILDREN];
+    __shared__ float s_prior[UNIFORM_PRIOR ? 1 : 4][UNIFORM_PRIOR ? 1 : QZ_SEL_MAX_CHILDREN];
+    const int wib = threadIdx.x >> 5;
+    const int rbase = child_base[root];
+    uint32_t rmeta = 0;
+    int rnc = 0, rvis = 0, root_marks = 0;
+    if (rbase >= 0) {
+        rmeta = meta[root];
+        rnc = qz_meta_nchild(rmeta);
+        rvis = visits[root];
+        for (int j = lane; j < rnc; j += 32) {
+            s_n[wib][j] = visits[rbase + j];
+            s_meta[wib][j] = meta[rbase + j];
+            s_q[wib][j] = q[rbase + j];
+            if (!UNIFORM_PRIOR) s_prior[wib][j] = prior[rbase + j];
+        }
+    }
+    __syncwarp();
     for (int k = 0; k < K; k++) {
         const int64_t L = g * K + k;
         if (k >= k_leaves) {
@@ -83,26 +107,33 @@ __global__ void __launch_bounds__(128) qz_mcts_select_kernel(qz_tree t, double c
         int node = root, depth = 0;
         unsigned flags = 0;
         if (lane == 0) { path[0] = node; meta[root] += (1u << 16); }   // every node on the path carries one in-flight mark
+        root_marks++;
         __syncwarp();
         for (;;) {
-            const int base = child_base[node];
+            const bool at_root = depth == 0;
+            const int base = at_root ? rbase : child_base[node];
             if (base < 0) break;                                        // is_leaf (mcts.py:76)
-            const uint32_t pm = meta[node];
+            const uint32_t pm = at_root ? rmeta + ((uint32_t)root_marks << 16) : meta[node];
             const int nc = qz_meta_nchild(pm);
-            const int np_eff = visits[node] + qz_meta_inflight(pm) - 1;  // minus this descent's own mark
+            const int np_eff = (at_root ? rvis : visits[node]) + qz_meta_inflight(pm) - 1;  // minus this descent's own mark
             const double sq = sqrt((double)np_eff);                     // np.sqrt(parent._n_visits)
             const double uni = UNIFORM_PRIOR ? c_puct * (1.0 / (double)nc) : 0.0;   // pure_mcts.py:15
             double best = -INFINITY;
             int bj = 0x7FFFFFFF;
             for (int j = lane; j < nc; j += 32) {
                 const int c = base + j;
-                const uint32_t cm = meta[c];
-                const int n = visits[c], infl = qz_meta_inflight(cm);
-                double qv = q[c];
-                if (infl > 0) qv = (qv * (double)n - (double)infl) / (double)(n + infl);   // virtual loss (K > 1 only)
+                const uint32_t cm = at_root ? s_meta[wib][j] : meta[c];
+                const int n = at_root ? s_n[wib][j] : visits[c], infl = qz_meta_inflight(cm);
+                double qv = at_root ? s_q[wib][j] : q[c];
+                if (infl > 0) {                                         // virtual loss (K > 1 only)
+                    // a zero numerator (e.g. one win, one mark) would send the FP64 division down its ~100-instruction
+                    // special-case path, which was a quarter of this kernel's instructions; 0 / x is +0 either way
+                    const double num = qv * (double)n - (double)infl;
+                    qv = num == 0.0 ? 0.0 : num / (double)(n + infl);
+                }
                 double cp;
                 if (UNIFORM_PRIOR) cp = uni;
-                else cp = (double)((float)c_puct * prior[c]);           // float32 product first (numpy weak scalar)
+                else cp = (double)((float)c_puct * (at_root ? s_prior[wib][j] : prior[c]));   // float32 product first (numpy weak scalar)
                 const double u = cp * sq / (double)(1 + n + infl);      // mcts.py:69
                 const double v = qv + u;
                 if (v > best) { best = v; bj = j; }                     // ascending j per lane: first max kept
@@ -115,10 +146,15 @@ __global__ void __launch_bounds__(128) qz_mcts_select_kernel(qz_tree t, double c
             }
             if (bj == 0x7FFFFFFF) bj = 0;                                // all-NaN guard; never in practice
             node = base + bj;
-            const uint32_t cm = meta[node];
+            const uint32_t cm = at_root ? s_meta[wib][bj] : meta[node];
             s = qz_apply(s, qz_meta_action(cm));                         // game.step(action), mcts.py:113
             depth++;
-            if (lane == 0) { path[depth] = node; meta[node] = cm + (1u << 16); }
+            __syncwarp();                                                // everyone has read s_meta[bj]
+            if (lane == 0) {
+                path[depth] = node;
+                meta[node] = cm + (1u << 16);
+                if (at_root) s_meta[wib][bj] = cm + (1u << 16);
+            }
             __syncwarp();
             if (depth >= t.max_depth - 1) { flags |= QZ_LEAF_DEPTH_OVERFLOW; break; }
         }

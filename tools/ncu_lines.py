@@ -61,15 +61,16 @@ def main():
     hdr = next(i for i in range(start, len(rows)) if rows[i] and rows[i][0] == "Address")
     h = rows[hdr]
     ia, ii, it = h.index("Address"), h.index("Instructions Executed"), h.index("Thread Instructions Executed")
+    isamp = h.index("Warp Stall Sampling (All Samples)") if "Warp Stall Sampling (All Samples)" in h else None
     insts = []
     for r in rows[hdr + 1:]:
         if len(r) != len(h) or r[0] in ("Address", "Kernel Name"):
             break
-        insts.append((int(r[ia], 16), int(r[ii]), int(r[it])))
+        insts.append((int(r[ia], 16), int(r[ii]), int(r[it]), int(r[isamp]) if isamp is not None and r[isamp].isdigit() else 0))
     base = insts[0][0]
     table = {off: (txt, fr) for off, txt, fr in line_table(kern)}
-    agg, tot, ttot = {}, 0, 0
-    for addr, n, tn in insts:
+    agg, tot, ttot, stot = {}, 0, 0, 0
+    for addr, n, tn, sm in insts:
         txt, fr = table.get(addr - base, ("?", []))
         key = ("?", 0)
         if fr:
@@ -80,20 +81,23 @@ def main():
                         key = f
                         if inner:
                             break
-        a = agg.setdefault(key, [0, 0])
+        a = agg.setdefault(key, [0, 0, 0])
         a[0] += n
         a[1] += tn
+        a[2] += sm
         tot += n
         ttot += tn
+        stot += sm
     print("# %s: %d warp instructions, %.2f threads/instruction" % (kern, tot, ttot / max(tot, 1)))
     src_cache = {}
-    for key, (n, tn) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:40]:
+    by = 2 if os.environ.get("SORT_BY_STALL") else 0      # SORT_BY_STALL=1: rank by warp-stall samples (latency-bound kernels)
+    for key, (n, tn, sm) in sorted(agg.items(), key=lambda kv: -kv[1][by])[:40]:
         f, l = key
         if f not in src_cache:
             p = glob.glob(os.path.join(ROOT, "alphazero_quoridor_b200", "csrc", f))
             src_cache[f] = open(p[0]).read().split("\n") if p else []
         text = src_cache[f][l - 1].strip()[:90] if 0 < l <= len(src_cache[f]) else ""
-        print("%5.1f%%  %5.1f thr  %s:%d  %s" % (100.0 * n / tot, tn / max(n, 1), f, l, text))
+        print("%5.1f%% inst  %5.1f%% stall  %5.1f thr  %s:%d  %s" % (100.0 * n / tot, 100.0 * sm / max(stot, 1), tn / max(n, 1), f, l, text))
 
 
 if __name__ == "__main__":
