@@ -263,21 +263,26 @@ __global__ void __launch_bounds__(128) qz_mcts_expand_backup_kernel(qz_tree t, Q
             __syncwarp();
             continue;
         }
-        if (lane == 0) {
+        {
+            // update_recursive(-leaf_value), mcts.py:56-62,127: the nodes of one path are distinct, so lane d updates
+            // the node at depth d (one memory latency per leaf instead of one per level); leaves are still backed up
+            // one after the other, so every node sees its updates in playout order as in the reference
             const int32_t *path = t.path + L * t.max_depth;
             const int len = t.path_len[L];
-            double x = -v;                                               // update_recursive(-leaf_value), mcts.py:127
-            for (int d = len - 1; d >= 0; d--) {
-                const int nd = path[d];
-                const int nv = visits[nd] + 1;
-                visits[nd] = nv;
-                const double qo = q[nd];
-                q[nd] = qo + 1.0 * (x - qo) / (double)nv;                // mcts.py:53
-                if (d > 0) meta[nd] -= (1u << 16);                       // clear this descent's virtual loss
-                x = -x;                                                  // mcts.py:61
+            for (int d0 = 0; d0 < len; d0 += 32) {
+                const int d = d0 + lane;
+                if (d < len) {
+                    const int nd = path[d];
+                    const double x = ((len - 1 - d) & 1) ? v : -v;       // the sign flips per level (mcts.py:61)
+                    const int nv = visits[nd] + 1;
+                    visits[nd] = nv;
+                    const double qo = q[nd];
+                    const double num = 1.0 * (x - qo);
+                    q[nd] = num == 0.0 ? qo + 0.0 : qo + num / (double)nv;   // mcts.py:53 (0 / n spared: FP64 special-case path)
+                    meta[nd] -= (1u << 16);                              // clear this descent's virtual loss
+                }
             }
-            meta[root] -= (1u << 16);
-            t.leaf_flags[L] = (uint8_t)flags;
+            if (lane == 0) t.leaf_flags[L] = (uint8_t)flags;
         }
         __syncwarp();
     }
