@@ -133,6 +133,10 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
 #define QZ_STUCK_THREADS 32
 #endif
 __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
+    // the ordered superset S of the ply (qz_sample.cuh) as a byte table, built by the warp once per ply: decoding an
+    // attempt is then one shared-memory load instead of a k-th-set-bit search on every lane in every round
+    __shared__ uint8_t s_superset[QZ_STUCK_THREADS / 32][144];
+    uint8_t *superset = s_superset[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     for (;;) {
         unsigned long long k = 0;
@@ -158,10 +162,25 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs 
                 act = qz_nth_bit64((uint64_t)pawn, (int)qz_mulhi32(qz_attempt_word(rng, (uint32_t)steps, 0), M));
             } else if (M != 0) {
                 const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
+                __syncwarp();                                           // the previous ply's table is no longer read
+#pragma unroll
+                for (int q = 0; q < 5; q++) {
+                    const int act_q = lane + 32 * q;                    // actions 0..139 over five passes
+                    if (act_q < 12) {
+                        if ((pawn >> act_q) & 1u) superset[__popc(pawn & ((1u << act_q) - 1u))] = (uint8_t)act_q;
+                    } else if (act_q < 76) {
+                        const int ix = act_q - 12;
+                        if ((hc >> ix) & 1ull) superset[npawn + __popcll(hc & ((1ull << ix) - 1ull))] = (uint8_t)act_q;
+                    } else if (act_q < 140) {
+                        const int ix = act_q - 76;
+                        if ((vc >> ix) & 1ull) superset[npawn + nh + __popcll(vc & ((1ull << ix) - 1ull))] = (uint8_t)act_q;
+                    }
+                }
+                __syncwarp();
                 uint64_t bad_h = 0, bad_v = 0;                          // walls already known to block (warp-uniform)
                 for (uint32_t round = 0; act < 0; round++) {
                     const uint32_t word = qz_attempt_word(rng, (uint32_t)steps, round * 32 + lane);
-                    const int cand = qz_superset_action(pawn, hc, vc, npawn, nh, (int)qz_mulhi32(word, M));
+                    const int cand = superset[qz_mulhi32(word, M)];
                     const unsigned pawn_lanes = __ballot_sync(QZ_FULL_MASK, cand < 12);
                     const int first_pawn = pawn_lanes ? __ffs(pawn_lanes) - 1 : 32;
                     bool ok = false;

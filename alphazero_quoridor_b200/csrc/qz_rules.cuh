@@ -97,11 +97,22 @@ QZ_HD uint32_t qz_fshr(uint32_t lo, uint32_t hi, int k) {   // low word of ((hi:
 // index of the k-th (0-based) set bit of m; m must have more than k bits set
 QZ_HD int qz_nth_bit64(uint64_t m, int k) {
 #if defined(__CUDA_ARCH__)
+    // binary search on popcounts of the low half / byte / nibble / pair (the __fns intrinsic is ~45 instructions and
+    // sat on the critical path of every draw of the rollout kernels)
     uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
-    int cl = __popc(lo);
-    uint32_t w = lo; int base = 0;
-    if (k >= cl) { k -= cl; w = hi; base = 32; }
-    return base + (int)__fns(w, 0, k + 1);
+    int c = __popc(lo);
+    uint32_t w = lo; int r = 0;
+    if (k >= c) { k -= c; w = hi; r = 32; }
+    c = __popc(w & 0xFFFFu);
+    if (k >= c) { k -= c; w >>= 16; r += 16; }
+    c = __popc(w & 0xFFu);
+    if (k >= c) { k -= c; w >>= 8; r += 8; }
+    c = __popc(w & 0xFu);
+    if (k >= c) { k -= c; w >>= 4; r += 4; }
+    c = __popc(w & 0x3u);
+    if (k >= c) { k -= c; w >>= 2; r += 2; }
+    if (k >= (int)(w & 1u)) r += 1;
+    return r;
 #else
     for (int i = 0; i < k; i++) m &= m - 1;
     return __builtin_ctzll(m);
