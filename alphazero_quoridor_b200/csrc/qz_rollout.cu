@@ -68,9 +68,11 @@ __device__ __forceinline__ int64_t qz_start_index(const QzRolloutArgs &a, int64_
 // legal placement) is under 1 % of the rollouts but cost 60 % of all path checks and, worse, a serial tail:
 // hundreds of plies of up to 40 rejected draws each on ONE lane (profiles/r1b_rollout_wall_ncu_full.txt: SMs
 // active 15 % of the kernel's duration).  Such a rollout is therefore EJECTED from this kernel after
-// QZ_MAX_REJECTS failed draws in one ply and finished by qz_rollout_stuck_kernel, where a whole block sweeps
-// all candidates of a ply in parallel.
+// QZ_MAX_REJECTS failed draws in one ply and finished by qz_rollout_stuck_kernel, where a whole warp evaluates
+// the draw attempts of a ply in parallel.
+#ifndef QZ_MAX_REJECTS
 #define QZ_MAX_REJECTS 2u
+#endif
 
 __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a) {
     QzState s;
