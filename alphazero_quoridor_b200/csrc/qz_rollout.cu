@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs 
     // the ordered superset S of the ply (qz_sample.cuh) as a byte table, built by the warp once per ply: decoding an
     // attempt is then one shared-memory load instead of a k-th-set-bit search on every lane in every round
     __shared__ uint8_t s_superset[QZ_STUCK_THREADS / 32][144];
+    // the corner masks of the current walls: a stuck rollout plays hundreds of plies between two wall placements,
+    // so they are parked here and reloaded (36 broadcast loads) instead of rebuilt (~250 instructions) every ply
+    __shared__ uint32_t s_ctx[QZ_STUCK_THREADS / 32][QZ_CTX_WORDS];
     uint8_t *superset = s_superset[threadIdx.x >> 5];
+    uint32_t *ctx_words = s_ctx[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
     for (;;) {
         unsigned long long k = 0;
@@ -151,9 +155,20 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs 
         const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, r)) + 2);
         int steps = (int)qz_ply(s.meta) - (int)qz_ply(m0);
         QzRng rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + r) : a.rid_base + (uint64_t)r);
+        uint64_t ctx_h = 0, ctx_v = 0;
+        bool ctx_parked = false;
         for (;;) {
             if (qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0) break;
-            const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+            QzPawnCtx c;
+            if (ctx_parked && ctx_h == s.H && ctx_v == s.V) {
+                c = qz_ctx_load(ctx_words);
+            } else {
+                c = qz_ctx_build(s.H, s.V);
+                __syncwarp();
+                if (lane == 0) qz_ctx_store(c, ctx_words);
+                __syncwarp();
+                ctx_h = s.H; ctx_v = s.V; ctx_parked = true;
+            }
             const uint32_t pawn = qz_mover_pawn_moves_ctx(c, s.meta);
             const bool has_walls = qz_mover_walls(s.meta) > 0;
             const uint64_t hc = has_walls ? qz_hcand(s.H, s.V) : 0ull, vc = has_walls ? qz_vcand(s.H, s.V) : 0ull;

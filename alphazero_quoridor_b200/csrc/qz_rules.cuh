@@ -368,6 +368,22 @@ QZ_HD QzPawnCtx qz_ctx_build(uint64_t H, uint64_t V) {
     return c;
 }
 
+// the twelve masks as 36 words (for parking a ctx in shared memory while the walls do not change)
+#define QZ_CTX_WORDS 36
+#define QZ_CTX_EACH(F) F(d.n, 0) F(d.s, 1) F(d.e, 2) F(d.w, 3) F(neV, 4) F(nwV, 5) F(seV, 6) F(swV, 7) F(neH, 8) F(nwH, 9) F(seH, 10) F(swH, 11)
+QZ_HD void qz_ctx_store(const QzPawnCtx &c, uint32_t *w) {
+#define QZ_CTX_ST(m, i) w[3 * i] = c.m.w0; w[3 * i + 1] = c.m.w1; w[3 * i + 2] = c.m.w2;
+    QZ_CTX_EACH(QZ_CTX_ST)
+#undef QZ_CTX_ST
+}
+QZ_HD QzPawnCtx qz_ctx_load(const uint32_t *w) {
+    QzPawnCtx c;
+#define QZ_CTX_LD(m, i) c.m.w0 = w[3 * i]; c.m.w1 = w[3 * i + 1]; c.m.w2 = w[3 * i + 2];
+    QZ_CTX_EACH(QZ_CTX_LD)
+#undef QZ_CTX_LD
+    return c;
+}
+
 // quoridor.py:272-353 without a branch.  L on the board; any O (an off-board O is never adjacent).
 QZ_HD uint32_t qz_pawn_moves_ctx(const QzPawnCtx &c, int L, int O, int player) {
     const uint32_t ovalid = (unsigned)O <= 80u ? 1u : 0u;
