@@ -346,11 +346,11 @@ def run_ours(args):
     avg_ms = avg_main + avg_stuck
     avg_n = sum(roll_n) / max(len(roll_n), 1)
     achieved = bytes_per_rollout * avg_n / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    # whole-step warp-instruction count from the committed launch list of this same command (profiles/r1o_bench_launches.txt:
-    # 382.15 G warp instructions over 7 steps of 4096 games x 1000 playouts), scaled to this run's playouts per step
+    # whole-step warp-instruction count from the committed launch list of this same command (profiles/r1p_bench_launches.txt:
+    # 378.10 G warp instructions over 7 steps of 4096 games x 1000 playouts), scaled to this run's playouts per step
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     issue_peak = sm_count * 4 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6           # warp instructions / s
-    inst_per_step = 382.15e9 / 7.0 * (args.games * args.playouts) / (4096.0 * 1000.0)
+    inst_per_step = 378.10e9 / 7.0 * (args.games * args.playouts) / (4096.0 * 1000.0)
     roofline = {"kernel": "qz_rollout_wall_kernel + qz_rollout_pawn_kernel passes (waves) + qz_rollout_stuck_kernel (end of search)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak,
@@ -361,7 +361,7 @@ def run_ours(args):
                 "launches_timed": len(roll_ms), "avg_launch_ms": avg_ms, "avg_main_stream_ms": avg_main,
                 "avg_deferred_stuck_pass_ms": avg_stuck, "rollouts_per_launch": avg_n,
                 "share_of_step": (sum(roll_ms) + sum(stuck_ms)) / ms if ms > 0 else None,
-                "issue_profile": {"source": "profiles/r1o_bench_launches.txt, profiles/r1m_rollout_ncu_full.txt, "
+                "issue_profile": {"source": "profiles/r1p_bench_launches.txt, profiles/r1m_rollout_ncu_full.txt, "
                                             "profiles/r1m_sweep_ncu_full.txt (ncu, B200)",
                                   "whole_step": {"warp_instructions": inst_per_step,
                                                  "achieved_warp_inst_per_s": inst_per_step / (ms / args.steps * 1e-3) if ms > 0 else None,
@@ -369,9 +369,9 @@ def run_ours(args):
                                                  "frac": inst_per_step / (ms / args.steps * 1e-3) / issue_peak if ms > 0 else None,
                                                  "note": "instruction count from the committed launch list (static), time from "
                                                          "this run; the ALU-pipe-bound kernels below reach 0.60-0.76 alone"},
-                                  "instruction_share": {"qz_rollout_stuck_kernel": 0.297, "qz_legal_mask_kernel": 0.259,
-                                                        "qz_rollout_pawn_kernel": 0.196, "qz_rollout_wall_kernel": 0.122,
-                                                        "qz_mcts_select_kernel": 0.088, "qz_mcts_expand_backup_kernel": 0.036},
+                                  "instruction_share": {"qz_rollout_stuck_kernel": 0.290, "qz_legal_mask_kernel": 0.262,
+                                                        "qz_rollout_pawn_kernel": 0.199, "qz_rollout_wall_kernel": 0.123,
+                                                        "qz_mcts_select_kernel": 0.089, "qz_mcts_expand_backup_kernel": 0.037},
                                   "smsp_issue_active_pct": {"qz_rollout_wall_kernel": 60.8, "qz_rollout_pawn_kernel (first pass)": 76.0,
                                                             "qz_rollout_stuck_kernel": 43.3, "qz_legal_mask_kernel": 62.8},
                                   "active_lanes_per_instruction": {"qz_rollout_wall_kernel": 18.6, "qz_rollout_pawn_kernel": 23.7,
