@@ -99,7 +99,15 @@ __global__ void __launch_bounds__(128, 7) qz_mcts_select_kernel(qz_tree t, doubl
     for (int k = 0; k < K; k++) {
         const int64_t L = g * K + k;
         if (k >= k_leaves) {
-            if (lane == 0) { t.leaf_flags[L] = QZ_LEAF_INACTIVE; t.path_len[L] = 0; t.leaf_node[L] = -1; }
+            // an unused leaf slot gets a finished position: the legality sweep and the rollout kernels that run over
+            // all n*K slots then drop it at once (the one-leaf first wave of a search would otherwise evaluate the
+            // stale positions of 63 slots per game -- a whole wave's work)
+            if (lane == 0) {
+                t.leaf_flags[L] = QZ_LEAF_INACTIVE; t.path_len[L] = 0; t.leaf_node[L] = -1;
+                QzState idle;
+                idle.H = 0; idle.V = 0; idle.meta = qz_pack_meta(4, 76, 0, 0, 1, QZ_FLAG_DONE, 0);
+                qz_store_state(t.leaf_state + L, idle);
+            }
             continue;
         }
         int32_t *__restrict__ path = t.path + L * t.max_depth;
