@@ -346,11 +346,13 @@ def run_ours(args):
     avg_ms = avg_main + avg_stuck
     avg_n = sum(roll_n) / max(len(roll_n), 1)
     achieved = bytes_per_rollout * avg_n / (avg_ms * 1e-3) / 1e9 if avg_ms > 0 else 0.0
-    # whole-step warp-instruction count from the committed launch list of this same command (profiles/r1p_bench_launches.txt:
-    # 378.10 G warp instructions over 7 steps of 4096 games x 1000 playouts), scaled to this run's playouts per step
+    # whole-step warp-instruction count from the committed launch list of this same command (profiles/r1p_bench_launches.txt,
+    # 7 steps of 17 waves x 262,144 leaf slots): the sweep and rollout kernels executed 47.17 G warp instructions per step
+    # = 10,585 per leaf slot, select + expand 6.81 G per step.  Since r1q unused leaf slots cost (next to) nothing, so the
+    # per-slot figure is applied to the playouts actually made.
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     issue_peak = sm_count * 4 * float(peaks.get("sm_max_mhz", 1965.0)) * 1e6           # warp instructions / s
-    inst_per_step = 378.10e9 / 7.0 * (args.games * args.playouts) / (4096.0 * 1000.0)
+    inst_per_step = 10585.0 * args.games * args.playouts + 6.81e9 * (args.games * args.playouts) / (4096.0 * 1000.0)
     roofline = {"kernel": "qz_rollout_wall_kernel + qz_rollout_pawn_kernel passes (waves) + qz_rollout_stuck_kernel (end of search)",
                 "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak,
