@@ -268,6 +268,28 @@ def test_sharding_invariance(qz):
         assert torch.equal(whole[t][1], torch.cat([parts[0][t][1], parts[1][t][1]]))
 
 
+def test_unused_leaf_slots_are_idle(qz):
+    """A wave that collects fewer than K leaves per game (the first wave of a search: one) must not evaluate the
+    other slots: they hold a finished position, cost no rollout plies and leave the tree untouched."""
+    n, K = 96, 8
+    start = qz.q.BatchedQuoridor(n).states
+    played = []
+    for k_leaves in (1, K):
+        ev = qz.tree.RolloutEvaluator(seed=5)
+        eng = qz.tree.BatchedMCTS(n, ev, c_puct=5, n_playout=2 * K, leaves_per_game=k_leaves, reuse_tree=False)
+        eng.reset(start)
+        eng.playout_wave(1)
+        torch.cuda.synchronize()
+        played.append(ev.plies_played())
+        if k_leaves == K:
+            flags = eng.leaf_flags.view(n, K).cpu().numpy()
+            meta = eng.leaf_state.view(n, K, 3)[:, :, 2].cpu().numpy()
+            assert (flags[:, 0] & qz.tree.LEAF_INACTIVE == 0).all() and (flags[:, 1:] & qz.tree.LEAF_INACTIVE != 0).all()
+            assert (((meta[:, 1:] >> 40) & 1) == 1).all()                 # idle slots: finished position
+            assert int(eng.arena.visits.view(n, -1)[:, 0].sum().item()) == n      # one backup per game
+    assert played[0] == played[1] and 0 < played[0] <= n * 999            # same rollouts as the K = 1 engine
+
+
 def test_deferred_stuck_rollouts(qz):
     """defer_depth=3: the stuck rollouts of a wave finish on a side stream and are backed up three waves later;
     defer_until_drain: the stuck rollouts of every wave are finished together when the search ends.
