@@ -135,12 +135,27 @@ class NetEvaluator:
     """Leaf evaluation by the policy-value net (policy_value_net.py:145-164 contract, batched).
     `net` is an alphazero_quoridor_b200.policy_value_net.PolicyValueNet."""
 
+    wants_k = True        # evaluate() takes the number of leaves per game this wave really collected
+
     def __init__(self, net):
         self.net = net
+        self._full = None
 
-    def evaluate(self, mcts, lset, leaf_rids):
-        probs, value = self.net.evaluate_states(lset.leaf_state)
-        return dict(priors=probs, value_f32=value)
+    def evaluate(self, mcts, lset, leaf_rids, k_leaves=None):
+        m = lset.leaf_state.shape[0]
+        if k_leaves is None or k_leaves >= mcts.K:
+            probs, value = self.net.evaluate_states(lset.leaf_state)
+            return dict(priors=probs, value_f32=value)
+        # a wave with unused leaf slots (the first wave of a search collects one leaf per game): only the used slots go
+        # through the net; expansion never reads the rows of the others
+        idx = mcts.active_slots(k_leaves)
+        probs_c, value_c = self.net.evaluate_states(lset.leaf_state.index_select(0, idx))
+        if self._full is None or self._full[0].shape[0] != m:
+            self._full = (torch.zeros((m, probs_c.shape[1]), dtype=probs_c.dtype, device=probs_c.device),
+                          torch.zeros((m,), dtype=value_c.dtype, device=value_c.device))
+        self._full[0].index_copy_(0, idx, probs_c)
+        self._full[1].index_copy_(0, idx, value_c)
+        return dict(priors=self._full[0], value_f32=self._full[1])
 
 
 # ------------------------------------------------------------------------------------------------ the search
@@ -183,6 +198,7 @@ class BatchedMCTS:
         self.sets = [_LeafSet(m, self.max_depth, dev) for _ in range(max(1, self.defer_depth))]
         self.cur_set = 0
         self.wave_index = 0
+        self._active_slots = {}
         # one side stream per leaf set: the stuck passes of consecutive waves are latency-bound (a few hundred
         # long-running blocks each) and must overlap each other, not only the main stream
         self.side_streams = [torch.cuda.Stream(device=dev) for _ in self.sets] if self.defer_depth >= 2 else []
@@ -199,6 +215,15 @@ class BatchedMCTS:
         self._structs = [[self._make_struct(a, ls) for ls in self.sets] for a in self.arenas]
 
     # ---- plumbing ----
+    def active_slots(self, k):
+        """Leaf-slot indices g*K + j (j < k) of a wave that collects k < K leaves per game (int64, cached)."""
+        idx = self._active_slots.get(k)
+        if idx is None:
+            g = torch.arange(self.n, dtype=torch.int64, device=self.device)[:, None] * self.K
+            idx = (g + torch.arange(k, dtype=torch.int64, device=self.device)[None, :]).reshape(-1)
+            self._active_slots[k] = idx
+        return idx
+
     def _stream(self):
         return _lib.stream_ptr(self.device)
 
@@ -313,7 +338,12 @@ class BatchedMCTS:
             rids = None
             if getattr(self.evaluator, "uniform_prior", False):
                 rids = (self.game_id.repeat_interleave(self.K) + (self.total_playouts + self._k_of_leaf))
-            ev = self.evaluator.evaluate(self, ls, rids, defer=True) if defer else self.evaluator.evaluate(self, ls, rids)
+            if defer:
+                ev = self.evaluator.evaluate(self, ls, rids, defer=True)
+            elif getattr(self.evaluator, "wants_k", False):
+                ev = self.evaluator.evaluate(self, ls, rids, k_leaves=k)
+            else:
+                ev = self.evaluator.evaluate(self, ls, rids)
             _lib.check(self.lib.qz_mcts_expand_backup(
                 C.byref(self.tree), _lib.ptr(ls.leaf_mask), _lib.ptr(ev.get("priors")),
                 _lib.ptr(ev.get("value_f32")), _lib.ptr(ev.get("value_f64")), _lib.ptr(ev.get("value_i8")),
