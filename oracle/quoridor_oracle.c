@@ -522,11 +522,6 @@ void oq_philox(uint64_t seed, uint64_t rid, uint32_t c2, uint32_t c3, uint32_t *
     philox4x32_10(ctr, key, out4);
 }
 
-static int nth_set_bit64(uint64_t m, int k) {
-    for (int i = 0; i < 64; i++) if ((m >> i) & 1) { if (k == 0) return i; k--; }
-    return -1;
-}
-
 /*
  * One uniformly random legal action (pure_mcts.py:7-10 + :99: argmax of iid U(0,1) over the legal list == a
  * uniform pick), by the draw procedure the product specifies (csrc/qz_sample.cuh) restated on top of the
