@@ -1,5 +1,6 @@
 """Per-call durations with a device synchronize after every call (nothing overlaps): separates what a kernel costs
-from what concurrency does to it.  Usage: python tools/serial_spans.py DEFER"""
+from what concurrency does to it.  Usage: python tools/serial_spans.py DEFER
+(DEFER = waves a stuck pass may lag; 0 = finished in-wave)"""
 import sys, os, collections, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alphazero_quoridor_b200 import tree, _lib
@@ -33,7 +34,7 @@ class Proxy:
 
 
 sp = StreamedSelfPlay(4096, lambda: tree.RolloutEvaluator(seed=1), n_streams=1, n_playout=1000, c_puct=5.0,
-                      leaves_per_game=64, pure=True, seed=1, defer_depth=defer)
+                      leaves_per_game=64, pure=True, seed=1, defer_depth=max(defer, 0), defer_until_drain=defer < 0)
 for _ in range(3):
     sp.step()
 torch.cuda.synchronize()

@@ -1,3 +1,6 @@
+"""Total-variation distance of root visit distributions, K leaves per wave (virtual loss) against K = 1, at the
+bench's search size (1000 playouts) under the deterministic stubs S1 (uniform priors, value 0 -- pure MCTS's
+priors) and S2 (pseudo-random priors and values).  DESIGN.md section 2 quotes its output.  Usage: python tools/tv_vs_k.py"""
 import sys, os, torch, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from alphazero_quoridor_b200 import tree
