@@ -68,6 +68,33 @@ unsigned qh_pawn_moves_info(uint64_t H, uint64_t V, int L, int O, int player) {
     return qz_pawn_moves_info(b[L], b[O], hO, L, O, player);
 }
 
+// the byte-per-tile table of the pawn-phase kernel next to the same eight bits read straight from the ctx masks
+void qh_tile_table(uint64_t H, uint64_t V, unsigned char *table84, unsigned char *direct81) {
+    QzPawnCtx c = qz_ctx_build(H, V);
+    uint32_t tbl[QZ_TILE_TABLE_WORDS];
+    qz_tile_table(c, tbl, 1);
+    for (int i = 0; i < 84; i++) table84[i] = reinterpret_cast<const unsigned char *>(tbl)[i];
+    for (int t = 0; t < 81; t++)
+        direct81[t] = (unsigned char)(bb_at(c.d.n, t) | (bb_at(c.d.s, t) << 1) | (bb_at(c.d.e, t) << 2) | (bb_at(c.d.w, t) << 3) |
+                                      (bb_at(c.neV, t) << 4) | (bb_at(c.nwV, t) << 5) | (bb_at(c.seV, t) << 6) | (bb_at(c.swV, t) << 7));
+}
+// qz_ctx_store / qz_ctx_load round trip (the stuck kernel parks the masks in shared memory)
+int qh_ctx_roundtrip(uint64_t H, uint64_t V) {
+    QzPawnCtx c = qz_ctx_build(H, V);
+    uint32_t w[QZ_CTX_WORDS];
+    qz_ctx_store(c, w);
+    QzPawnCtx d = qz_ctx_load(w);
+    int ok = 1;
+    for (int L = 0; L < 81; L++)
+        for (int k = 0; k < 4; k++) {
+            const int O = L + (k == 0 ? 9 : (k == 1 ? -9 : (k == 2 ? 1 : -1)));
+            if (O < 0 || O > 80) continue;
+            ok &= qz_pawn_moves_ctx(c, L, O, 1) == qz_pawn_moves_ctx(d, L, O, 1);
+            ok &= qz_pawn_moves_ctx(c, L, O, 2) == qz_pawn_moves_ctx(d, L, O, 2);
+        }
+    return ok;
+}
+
 void qh_dirs_ctx(uint64_t H, uint64_t V, unsigned char *out81) {
     QzPawnCtx c = qz_ctx_build(H, V);
     for (int t = 0; t < 81; t++)

@@ -345,3 +345,18 @@ def test_philox_and_rollouts_match_oracle(qh):
 
 
 M64 = (1 << 64) - 1
+
+
+def test_tile_table_is_the_transpose_of_the_masks(qh):
+    """qz_tile_table (four tiles per multiply) == the eight mask bits of every tile; tiles 81..83 stay empty;
+    qz_ctx_store / qz_ctx_load keep every mask."""
+    qh.qh_tile_table.argtypes = [C.c_uint64, C.c_uint64, C.c_char_p, C.c_char_p]
+    qh.qh_ctx_roundtrip.argtypes = [C.c_uint64, C.c_uint64]
+    rng = random.Random(23)
+    for it in range(400):
+        H, V = rand_walls(rng, rng.randrange(0, 30))
+        tab, direct = C.create_string_buffer(84), C.create_string_buffer(81)
+        qh.qh_tile_table(H, V, tab, direct)
+        assert tab.raw[:81] == direct.raw and tab.raw[81:] == b"\0\0\0"
+        if it % 8 == 0:
+            assert qh.qh_ctx_roundtrip(H, V) == 1
