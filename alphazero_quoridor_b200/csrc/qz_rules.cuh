@@ -634,7 +634,10 @@ QZ_HD QzState qz_apply(QzState s, int action) {
         if (cur == 1) p1 += dlt; else p2 += dlt;
     } else {
         int a = action - 12;
-        if (a < 64) s.H |= 1ull << a; else s.V |= 1ull << (a - 64);
+        // quoridor.py:246-257 assigns the cell (+1 / -1): an unchecked placement on an occupied intersection
+        // (safe=False) REPLACES the wall that was there
+        if (a < 64) { s.H |= 1ull << a; s.V &= ~(1ull << a); }
+        else { s.V |= 1ull << (a - 64); s.H &= ~(1ull << (a - 64)); }
         if (cur == 1) w1 -= 1; else w2 -= 1;
     }
     int winner = p2 < 9 ? 2 : (p1 > 71 ? 1 : 0);       // P2 tested first (:196-201)

@@ -183,9 +183,15 @@ class PolicyValueNet(object):
         return logp.exp().contiguous(), v.reshape(-1).contiguous()
 
     # ---- reference API ----
+    def _f32(self, x):
+        """numpy arrays / lists (the reference's inputs) or tensors already on the device -> float32 on self.device."""
+        if torch.is_tensor(x):
+            return x.to(device=self.device, dtype=torch.float32)
+        return torch.as_tensor(np.asarray(x), dtype=torch.float32, device=self.device)
+
     def policy_value(self, state_batch):
         """policy_value_net.py:127-143: [B,26,9,9] array -> (act_probs [B,140], value [B,1]) numpy."""
-        x = torch.as_tensor(np.asarray(state_batch), dtype=torch.float32, device=self.device)
+        x = self._f32(state_batch)
         with torch.no_grad():
             log_act_probs, value = self.policy_value_net(x)
         return np.exp(log_act_probs.cpu().numpy()), value.cpu().numpy()
@@ -208,10 +214,7 @@ class PolicyValueNet(object):
 
     def train_step(self, state_batch, mcts_probs, winner_batch, lr, grad_hook=None):
         """policy_value_net.py:166-192: loss = (z - v)^2 - pi^T log p (+ weight decay via Adam)."""
-        dev = self.device
-        state_batch = torch.as_tensor(np.asarray(state_batch), dtype=torch.float32, device=dev)
-        mcts_probs = torch.as_tensor(np.asarray(mcts_probs), dtype=torch.float32, device=dev)
-        winner_batch = torch.as_tensor(np.asarray(winner_batch), dtype=torch.float32, device=dev)
+        state_batch, mcts_probs, winner_batch = self._f32(state_batch), self._f32(mcts_probs), self._f32(winner_batch)
         self.policy_value_net.train()
         self.optimizer.zero_grad()
         set_learning_rate(self.optimizer, lr)

@@ -318,11 +318,12 @@ class Quoridor(object):
         return game_over, winner
 
     def _get_rewards(self):
-        """quoridor.py:205-214 (unused by the reference; its tuple-unpack bug at :208 is not reproduced)."""
+        """quoridor.py:205-214, literally (unused by the reference): (-1, 1) when P1 has won; when P2 has won the
+        reference's `rewards, done = (1, -1)` at :208 unpacks the tuple, so the call returns (1, -1) itself."""
         if self._positions[2] < 9:
-            return (-1, 1), True
+            return 1, -1
         if self._positions[1] > 71:
-            return (1, -1), True
+            return (-1, 1), True
         return (0, 0), False
 
     # quoridor.py:260-269

@@ -11,7 +11,7 @@ games gives the same results however it is sharded over GPUs (no collective on t
 import torch
 
 from .quoridor import BatchedQuoridor
-from .tree import BatchedMCTS, RolloutEvaluator
+from .tree import BatchedMCTS
 
 
 class BatchedSelfPlay:
@@ -30,28 +30,41 @@ class BatchedSelfPlay:
         self.n = self.mcts.n
         dev = self.device = self.mcts.device
         self.lib = self.mcts.lib
-        # games per slot so far; RNG stream of slot i's current game = (game_id_base + i) + n_slots_total * games_played
+        # games per slot so far; RNG stream id of slot i's current game = games_played << 20 | (game_id_base + i)
+        # (BatchedMCTS keys a rollout by (this id, playout counter), so ids only need to be distinct)
         self.game_id_base = int(game_id_base)
+        assert 0 <= self.game_id_base and self.game_id_base + self.n <= (1 << 20), "global game index must be < 2^20"
         self.games_started = torch.zeros(self.n, dtype=torch.int64, device=dev)
         self._slot = torch.arange(self.n, dtype=torch.int64, device=dev) + self.game_id_base
-        self.stride = 1 << 24            # rollout/RNG ids: game stream id * stride + playout counter
         self._start = BatchedQuoridor(1, device=dev).states
         self.mcts.reset(self._start.expand(self.n, 3).contiguous())
         self._set_game_ids()
         self.finished_games = torch.zeros((), dtype=torch.int64, device=dev)
         self.p1_wins = torch.zeros((), dtype=torch.int64, device=dev)
         self.truncated_games = torch.zeros((), dtype=torch.int64, device=dev)
+        self.stalemated_games = torch.zeros((), dtype=torch.int64, device=dev)
+        self.finished_plies = torch.zeros((), dtype=torch.int64, device=dev)     # plies of the finished games
         self.moves_played = 0
         if self.record:
             T = self.max_plies
             self.rec_state = torch.zeros((T, self.n, 3), dtype=torch.int64, device=dev)
             self.rec_probs = torch.zeros((T, self.n, 140), dtype=torch.float32, device=dev)
-            self.sink = []               # list of (states int64 [m,3], probs f32 [m,140], z f32 [m]) per flush
+            self._tgrid = torch.arange(T, device=dev)
+            # one entry per flush: (states int64 [m,3], probs f32 [m,140], z f32 [m], lengths int64 [games]) with the
+            # samples of a game contiguous and in ply order; a replay buffer consumes these as they are
+            self.flushed = []
 
     def _set_game_ids(self):
-        # a stream id unique per (slot, game-in-slot); shifted so per-playout counters never collide
-        gid = self._slot + self.games_started * (1 << 20)
-        self.mcts.game_id.copy_(gid * self.stride if isinstance(self.mcts.evaluator, RolloutEvaluator) else gid)
+        self.mcts.game_id.copy_((self.games_started << 20) | self._slot)
+
+    @property
+    def sink(self):
+        """The flushed samples split per finished game: [(states [T,3], probs [T,140], z [T]), ...]."""
+        out = []
+        for st, pr, z, lens in self.flushed:
+            ls = lens.tolist()
+            out.extend(zip(st.split(ls), pr.split(ls), z.split(ls)))
+        return out
 
     def wave_plan(self):
         """Leaves per wave of one move's search (mirrors BatchedMCTS.search)."""
@@ -87,45 +100,59 @@ class BatchedSelfPlay:
             self.rec_probs[t, idx] = probs.float()
         m.advance(moves, keep_subtree=not self.pure)
         self.moves_played += self.n
-        self._finish_games()
+        self._finish_games(moves)
         return moves
 
-    def _finish_games(self):
+    def _finish_games(self, moves):
         m = self.mcts
         meta = m.root_state[:, 2]
         done = ((meta >> 40) & 1).bool()
         ply = (meta >> 48) & 0xFFFF
         trunc = (~done) & (ply >= self.max_plies)
-        over = done | trunc
+        # a root whose mover has no legal action (QZ_FLAG_STALEMATE positions; the reference prints and returns None,
+        # mcts.py:195-196, then crashes in step): choose() gave -1 and nothing was played -- the game ends as a tie
+        stale = (~done) & (~trunc) & (moves < 0)
+        over = done | trunc | stale
         if self.record and not bool(over.any()):      # recording flushes on the host; otherwise stay asynchronous
             return
-        winner = (meta >> 41) & 3
+        winner = torch.where(done, (meta >> 41) & 3, torch.zeros_like(meta))
         self.finished_games += over.sum()
+        self.finished_plies += (ply * over).sum()
         self.p1_wins += (over & (winner == 1)).sum()
         self.truncated_games += trunc.sum()
+        self.stalemated_games += stale.sum()
         if self.record:
             self._flush(over, winner, ply)
+            self.check_overflow()
         sel = over.to(torch.uint8).contiguous()
         fresh = torch.where(over.unsqueeze(1), self._start.expand(self.n, 3), m.root_state).contiguous()
         m.reset(fresh, select=sel)            # fresh root + start position for the finished slots only
         self.games_started += over.to(torch.int64)
         self._set_game_ids()
 
+    def check_overflow(self):
+        """Arena overflows so far (an overflowing leaf stays unexpanded for that playout); warns once when non-zero.
+        Synchronises -- call it where the host waits anyway."""
+        n = self.mcts.overflow_count()
+        if n and not getattr(self, "_overflow_warned", False):
+            import warnings
+            warnings.warn("tree arena overflowed %d times: raise node_cap (now %d slots per game)" % (n, self.mcts.node_cap))
+            self._overflow_warned = True
+        return n
+
     def _flush(self, over, winner, ply):
-        """quoridor.py:596-610: z = +1 on the winner's plies, -1 on the loser's (0 for a truncated game)."""
+        """quoridor.py:596-610: z = +1 on the winner's plies, -1 on the loser's (0 for a game without a winner).
+        One gather for all finished games -- no per-game host loop."""
         idx = over.nonzero().flatten()
-        for g in idx.tolist():
-            T = int(min(int(ply[g].item()), self.max_plies))
-            if T == 0:
-                continue
-            st = self.rec_state[:T, g].clone()
-            pr = self.rec_probs[:T, g].clone()
-            mover = (st[:, 2] >> 32) & 0xFF
-            w = int(winner[g].item())
-            z = torch.zeros(T, dtype=torch.float32, device=self.device)
-            if w:
-                z = torch.where(mover == w, torch.ones_like(z), -torch.ones_like(z))
-            self.sink.append((st, pr, z))
+        T = ply[idx].clamp(max=self.max_plies)                                   # samples per finished game
+        keep = self._tgrid[None, :] < T[:, None]                                 # [games, T_max]
+        st = self.rec_state[:, idx].transpose(0, 1)[keep]                        # game-major, ply order
+        pr = self.rec_probs[:, idx].transpose(0, 1)[keep]
+        w = winner[idx][:, None].expand(-1, self.max_plies)[keep]
+        mover = (st[:, 2] >> 32) & 0xFF
+        z = torch.where(w == 0, 0.0, torch.where(mover == w, 1.0, -1.0)).to(torch.float32)
+        sel = T > 0
+        self.flushed.append((st, pr, z, T[sel]))
 
 
 class StreamedSelfPlay:

@@ -12,9 +12,6 @@ the only collective in the system -- and every rank collects its own shard of ga
 """
 from __future__ import print_function
 
-import random
-from collections import deque
-
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -73,9 +70,77 @@ def mirror_samples(states, probs):
     return out, probs[:, MIRROR_ACTION.to(probs.device)]
 
 
+class ReplayBuffer(object):
+    """`deque(maxlen=buffer_size)` of train.py:24 as a ring of device tensors: the 24-byte game state (re-encoded by
+    the encode kernel when a minibatch is drawn, instead of the float64 [26,9,9] array of quoridor.py:589), the 140
+    move probabilities and z.  Appends and sampling never leave the device and never loop over games."""
+
+    def __init__(self, maxlen, device):
+        self.maxlen = int(maxlen)
+        self.device = torch.device(device)
+        self.states = torch.zeros((self.maxlen, 3), dtype=torch.int64, device=self.device)
+        self.probs = torch.zeros((self.maxlen, 140), dtype=torch.float32, device=self.device)
+        self.z = torch.zeros((self.maxlen,), dtype=torch.float32, device=self.device)
+        self.size = 0           # valid entries
+        self.head = 0           # next slot to write (the oldest entry once the ring is full)
+
+    def __len__(self):
+        return self.size
+
+    def extend(self, states, probs, z):
+        """Append m samples (oldest entries are overwritten, like deque(maxlen))."""
+        m = states.shape[0]
+        if m == 0:
+            return
+        if m > self.maxlen:
+            states, probs, z = states[-self.maxlen:], probs[-self.maxlen:], z[-self.maxlen:]
+            m = self.maxlen
+        pos = (self.head + torch.arange(m, device=self.device)) % self.maxlen
+        self.states[pos] = states.to(self.device)
+        self.probs[pos] = probs.to(self.device, torch.float32)
+        self.z[pos] = z.to(self.device, torch.float32)
+        self.head = (self.head + m) % self.maxlen
+        self.size = min(self.maxlen, self.size + m)
+
+    def ordered(self):
+        """(states, probs, z) oldest first."""
+        if self.size < self.maxlen:
+            sl = slice(0, self.size)
+            return self.states[sl], self.probs[sl], self.z[sl]
+        idx = (self.head + torch.arange(self.maxlen, device=self.device)) % self.maxlen
+        return self.states[idx], self.probs[idx], self.z[idx]
+
+    def sample(self, batch_size, generator=None):
+        """`random.sample(buffer, batch_size)` (train.py:67): without replacement."""
+        assert batch_size <= self.size
+        perm = torch.randperm(self.size, generator=generator, device=self.device)[:batch_size]
+        if self.size == self.maxlen:
+            perm = (self.head + perm) % self.maxlen
+        return self.states[perm], self.probs[perm], self.z[perm]
+
+    def clear(self):
+        self.size = self.head = 0
+
+    def __getitem__(self, i):
+        st, pr, z = self.ordered()
+        return st[i], pr[i], float(z[i].item())
+
+
+def _dist_on():
+    return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+
+def broadcast_module(module, src=0):
+    """Every rank starts from rank `src`'s parameters AND buffers (BatchNorm running statistics)."""
+    if not _dist_on():
+        return
+    for t in list(module.parameters()) + list(module.buffers()):
+        dist.broadcast(t.data, src)
+
+
 class TrainPipeline(object):
     def __init__(self, init_model=None, n_parallel_games=256, leaves_per_game=4, device=None, seed=0,
-                 fix_terminal_sign=False, max_plies=600):
+                 fix_terminal_sign=False, max_plies=600, use_gpu=True, encode_fn=None):
         # train.py:17-31
         self.learn_rate = 2e-3
         self.lr_multiplier = 1.0
@@ -84,7 +149,6 @@ class TrainPipeline(object):
         self.c_puct = 5
         self.buffer_size = 10000
         self.batch_size = 128
-        self.data_buffer = deque(maxlen=self.buffer_size)
         self.play_batch_size = 1
         self.epochs = 5
         self.kl_targ = 0.02
@@ -92,17 +156,21 @@ class TrainPipeline(object):
         self.game_batch_num = 1500
         self.best_win_ratio = 0.0
         self.pure_mcts_playout_num = 1000
-        self.policy_value_net = PolicyValueNet(model_file=init_model, device=device) if init_model else \
-            PolicyValueNet(device=device)
+        self.policy_value_net = PolicyValueNet(model_file=init_model, device=device, use_gpu=use_gpu)
+        self.data_buffer = ReplayBuffer(self.buffer_size, self.policy_value_net.device)
         self.n_parallel_games = n_parallel_games
         self.leaves_per_game = leaves_per_game
         self.seed = seed
         self.fix_terminal_sign = fix_terminal_sign
         self.max_plies = max_plies
         self._selfplay = None
+        self._encode_fn = encode_fn              # tests on CPU ranks (gloo) supply their own; the product uses the kernel
         self.episode_len = 0
         self.rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self._gen = torch.Generator(device=self.policy_value_net.device)
+        self._gen.manual_seed(int(seed) * 7919 + self.rank)
+        broadcast_module(self.policy_value_net.policy_value_net)      # ranks must not start from different inits
 
     def _engine(self):
         if self._selfplay is None or self._selfplay.mcts.n_playout != self.n_playout:
@@ -114,41 +182,67 @@ class TrainPipeline(object):
         return self._selfplay
 
     def collect_selfplay_data(self, n_games=1, max_steps=100000):
-        """train.py:55-63: play until >= n_games more games have finished; extend the replay buffer."""
+        """train.py:55-63: play until >= n_games more games have finished; extend the replay buffer.  The samples
+        go from the self-play record tensors to the replay ring on the device (one append per flush)."""
         sp = self._engine()
-        target = len(sp.sink) + n_games
-        steps = 0
-        while len(sp.sink) < target and steps < max_steps:
+        finished = steps = 0
+        while finished < n_games and steps < max_steps:
             sp.step()
             steps += 1
-        finished, sp.sink = sp.sink, []
-        for st, pr, z in finished:
-            self.episode_len = st.shape[0]
-            st, pr, z = st.cpu(), pr.cpu(), z.cpu()
-            self.data_buffer.extend(zip(st.unbind(0), pr.unbind(0), z.tolist()))
-        return len(finished)
+            for st, pr, z, lens in sp.flushed:
+                self.data_buffer.extend(st, pr, z)
+                finished += int(lens.numel())
+                self.episode_len = int(lens[-1].item()) if lens.numel() else self.episode_len
+            sp.flushed = []
+        sp.check_overflow()
+        return finished
 
     def _encode(self, state_rows):
-        rows = torch.stack(list(state_rows)).to(self.policy_value_net.device)
+        """qz_state rows int64 [B,3] -> float32 planes [B,26,9,9] (quoridor.py:58-131) by the encode kernel."""
+        if self._encode_fn is not None:
+            return self._encode_fn(state_rows)
+        rows = state_rows.to(self.policy_value_net.device).contiguous()
         return BatchedQuoridor(rows.shape[0], states=rows, device=self.policy_value_net.device).encode(dtype=torch.float32)
 
     def _sync_gradients(self):
         allreduce_gradients(list(self.policy_value_net.policy_value_net.parameters()))
 
+    def _all_ranks(self, flag):
+        """True iff `flag` holds on EVERY rank (one MIN all-reduce): decisions that gate a collective must be collective."""
+        if not _dist_on():
+            return bool(flag)
+        t = torch.tensor([1.0 if flag else 0.0], device=self.policy_value_net.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item() > 0.5)
+
+    def _rank_mean(self, x):
+        if not _dist_on():
+            return float(x)
+        t = torch.tensor([float(x)], dtype=torch.float64, device=self.policy_value_net.device)
+        dist.all_reduce(t)
+        return float(t.item()) / dist.get_world_size()
+
+    def ready_to_update(self):
+        """train.py:100 `len(self.data_buffer) > self.batch_size`, on every rank."""
+        return self._all_ranks(len(self.data_buffer) > self.batch_size)
+
     def policy_update(self):
-        """train.py:65-92: <= 5 epochs on one minibatch, KL early stop, KL-adaptive learning-rate multiplier."""
-        mini_batch = random.sample(self.data_buffer, self.batch_size)
-        state_batch = self._encode([d[0] for d in mini_batch]).cpu().numpy()
-        mcts_probs_batch = np.stack([d[1].numpy() for d in mini_batch])
-        winner_batch = np.array([d[2] for d in mini_batch], dtype=np.float32)
-        old_probs, old_v = self.policy_value_net.policy_value(state_batch)
+        """train.py:65-92: <= 5 epochs on one minibatch, KL early stop, KL-adaptive learning-rate multiplier.
+        Multi-rank: every rank draws its own minibatch, gradients are averaged (one all-reduce per epoch), and the KL
+        that steers the early stop and the learning-rate multiplier is the mean over the ranks, so every rank makes the
+        same number of collective calls and keeps the same multiplier and weights."""
+        st, pr, z = self.data_buffer.sample(self.batch_size, generator=self._gen)
+        state_batch = self._encode(st)
+        net = self.policy_value_net
+        old_probs, old_v = net.policy_value(state_batch)
+        winner_batch = z.cpu().numpy()
         loss = entropy = kl = new_v = None
         for i in range(self.epochs):
-            loss, entropy = self.policy_value_net.train_step(state_batch, mcts_probs_batch, winner_batch,
-                                                             self.learn_rate * self.lr_multiplier,
-                                                             grad_hook=self._sync_gradients)
-            new_probs, new_v = self.policy_value_net.policy_value(state_batch)
+            loss, entropy = net.train_step(state_batch, pr, z, self.learn_rate * self.lr_multiplier,
+                                           grad_hook=self._sync_gradients)
+            new_probs, new_v = net.policy_value(state_batch)
             kl = np.mean(np.sum(old_probs * (np.log(old_probs + 1e-10) - np.log(new_probs + 1e-10)), axis=1))
+            kl = self._rank_mean(kl)
             if kl > self.kl_targ * 4:
                 break
         if kl > self.kl_targ * 2 and self.lr_multiplier > 0.1:
@@ -156,7 +250,7 @@ class TrainPipeline(object):
         elif kl < self.kl_targ / 2 and self.lr_multiplier < 10:
             self.lr_multiplier *= 1.5
         var = np.var(winner_batch)
-        self.last_stats = dict(kl=float(kl), lr_multiplier=self.lr_multiplier, loss=loss, entropy=entropy,
+        self.last_stats = dict(kl=float(kl), lr_multiplier=self.lr_multiplier, loss=loss, entropy=entropy, epochs=i + 1,
                                explained_var_old=float(1 - np.var(winner_batch - old_v.flatten()) / var) if var > 0 else 0.0,
                                explained_var_new=float(1 - np.var(winner_batch - new_v.flatten()) / var) if var > 0 else 0.0)
         return loss, entropy
@@ -168,13 +262,11 @@ class TrainPipeline(object):
         learning-rate multiplier and the replay buffer."""
         if model_name:
             self.policy_value_net.save_model(model_name)
-        buf = list(self.data_buffer)
+        st, pr, z = self.data_buffer.ordered()
         torch.save({"net": self.policy_value_net.get_policy_param(),
                     "optimizer": self.policy_value_net.optimizer.state_dict(),
                     "lr_multiplier": self.lr_multiplier,
-                    "buffer_states": torch.stack([b[0] for b in buf]) if buf else torch.zeros((0, 3), dtype=torch.int64),
-                    "buffer_probs": torch.stack([b[1] for b in buf]) if buf else torch.zeros((0, 140)),
-                    "buffer_z": torch.tensor([b[2] for b in buf], dtype=torch.float32)}, path)
+                    "buffer_states": st.cpu(), "buffer_probs": pr.cpu(), "buffer_z": z.cpu()}, path)
 
     def load_checkpoint(self, path):
         ck = torch.load(path, map_location=self.policy_value_net.device)
@@ -183,8 +275,8 @@ class TrainPipeline(object):
         self.policy_value_net._infer = None
         self.lr_multiplier = ck["lr_multiplier"]
         self.data_buffer.clear()
-        self.data_buffer.extend(zip(ck["buffer_states"].cpu().unbind(0), ck["buffer_probs"].cpu().unbind(0),
-                                    ck["buffer_z"].tolist()))
+        self.data_buffer.extend(ck["buffer_states"], ck["buffer_probs"], ck["buffer_z"])
+        broadcast_module(self.policy_value_net.policy_value_net)
 
     # ---- evaluation arena (the commented-out policy_evaluate of train.py:30-31,108) ----
     def policy_evaluate(self, n_games=64, n_playout=None, max_plies=300, seed=0):
@@ -222,7 +314,7 @@ class TrainPipeline(object):
         try:
             for i in range(self.game_batch_num):
                 self.collect_selfplay_data(self.play_batch_size)
-                if len(self.data_buffer) > self.batch_size:
+                if self.ready_to_update():              # collective decision: no rank may skip the all-reduces
                     loss, entropy = self.policy_update()
                     if self.rank == 0:
                         with open('loss.txt', 'a') as f:

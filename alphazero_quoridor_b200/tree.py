@@ -21,6 +21,8 @@ from .rollout import rollout as _rollout
 
 LEAF_TERMINAL, LEAF_DEPTH_OVERFLOW, LEAF_ARENA_OVERFLOW, LEAF_DUPLICATE, LEAF_INACTIVE, LEAF_PENDING = 1, 2, 4, 8, 16, 32
 MAX_CHILDREN = 140
+PLAYOUT_BITS = 24                      # rollout stream id = game_id << 24 | playout counter (mod 2^24)
+PLAYOUT_MASK = (1 << PLAYOUT_BITS) - 1
 
 
 class QzTree(C.Structure):
@@ -177,7 +179,8 @@ class BatchedMCTS:
         self.fix_terminal_sign = bool(fix_terminal_sign)
         self.max_depth = int(max_depth)
         if node_cap is None:
-            node_cap = 1 + (self.n_playout * (2 if reuse_tree else 1) + self.K) * 132
+            # an expansion adds at most 6 pawn moves + 128 walls; 140 = the action space (headroom for re-rooted subtrees)
+            node_cap = 1 + (self.n_playout * (2 if reuse_tree else 1) + self.K) * MAX_CHILDREN
         self.node_cap = int(node_cap)
         dev = self.device
         self.arenas = [_Arena(self.n, self.node_cap, dev)]
@@ -205,8 +208,9 @@ class BatchedMCTS:
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self._leaf_iota = torch.arange(m, dtype=torch.int32, device=dev)
         self._k_of_leaf = (torch.arange(m, dtype=torch.int64, device=dev) % self.K)
-        # RNG stream id of game g (rollouts, move sampling); callers set it to a GLOBAL game index so that
-        # results do not depend on how games are sharded over GPUs
+        # RNG stream id of game g (rollouts, move sampling); callers set it to a GLOBAL game index (< 2^40) so that
+        # results do not depend on how games are sharded over GPUs.  The Philox stream of a rollout is
+        # (game_id << 24) | (playout counter mod 2^24): unique per (game, playout) whatever ids the caller uses.
         self.game_id = torch.arange(self.n, dtype=torch.int64, device=dev)
         self.playouts_done = 0       # playouts since the last reset/advance (per game)
         self.total_playouts = 0
@@ -334,10 +338,12 @@ class BatchedMCTS:
                 self.tree_steps += (ls.path_len.clamp(min=1) - 1).sum()
             _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_mask), m, st),
                        "qz_env_legal_mask")
-            # rollout / RNG stream of leaf (g,k): unique per (game, playout)
+            # rollout / RNG stream of leaf (g,k): (game id, playout counter) in separate bit fields, so two games can
+            # never share a stream (pure_mcts.py:86-108 draws fresh randomness for every rollout)
             rids = None
             if getattr(self.evaluator, "uniform_prior", False):
-                rids = (self.game_id.repeat_interleave(self.K) + (self.total_playouts + self._k_of_leaf))
+                rids = ((self.game_id << PLAYOUT_BITS).repeat_interleave(self.K)
+                        | ((self.total_playouts + self._k_of_leaf) & PLAYOUT_MASK))
             if defer:
                 ev = self.evaluator.evaluate(self, ls, rids, defer=True)
             elif getattr(self.evaluator, "wants_k", False):

@@ -180,7 +180,7 @@ def test_pure_mcts_vs_oracle(qz):
     states = _positions(n, seed=31, min_plies=8, max_plies=50)
     ev = qz.tree.RolloutEvaluator(seed=seed)
     eng = qz.tree.BatchedMCTS(n, ev, c_puct=5, n_playout=n_playout, leaves_per_game=1, reuse_tree=False)
-    eng.game_id.copy_(torch.arange(n, dtype=torch.int64) << 32)
+    eng.game_id.copy_(torch.arange(n, dtype=torch.int64) + 1000)
     eng.reset(states)
     eng.search()
     visits, _, _ = eng.root_stats(temp=1.0)
@@ -189,7 +189,7 @@ def test_pure_mcts_vs_oracle(qz):
     hs, _, _, _ = _host(qz, states)
     for i, d in enumerate(hs):
         g = O.OracleGame().set_position(d["H"], d["V"], d["p1"], d["p2"], d["w1"], d["w2"], d["cur"])
-        o = O.OracleMCTS(0, 5, n_playout, seed=seed, rollout_counter=i << 32)
+        o = O.OracleMCTS(0, 5, n_playout, seed=seed, rollout_counter=(i + 1000) << 24)
         acts, v, _ = o.run(g)
         want = np.zeros(140, dtype=np.int32)
         want[acts] = v
@@ -306,7 +306,7 @@ def test_deferred_stuck_rollouts(qz):
     for defer, at_drain in ((0, False), (3, False), (3, False), (0, True), (0, True)):
         eng = qz.tree.BatchedMCTS(n, qz.tree.RolloutEvaluator(seed=11), c_puct=5, n_playout=n_playout,
                                   leaves_per_game=K, reuse_tree=False, defer_depth=defer, defer_until_drain=at_drain)
-        eng.game_id.copy_(torch.arange(n, dtype=torch.int64) << 32)
+        eng.game_id.copy_(torch.arange(n, dtype=torch.int64) + 1000)
         eng.reset(states)
         eng.search()
         visits, _, rootn = eng.root_stats(temp=1.0)

@@ -360,3 +360,18 @@ def test_tile_table_is_the_transpose_of_the_masks(qh):
         assert tab.raw[:81] == direct.raw and tab.raw[81:] == b"\0\0\0"
         if it % 8 == 0:
             assert qh.qh_ctx_roundtrip(H, V) == 1
+
+
+def test_unchecked_wall_on_occupied_intersection_replaces_it(qh):
+    """quoridor.py:246-257 assigns the cell, so with safe=False a wall placed on an occupied intersection REPLACES
+    the wall that stood there (the oracle's intersection array does the same)."""
+    for first, second in ((12 + 27, 76 + 27), (76 + 9, 12 + 9)):
+        g = O.OracleGame()
+        s = mk_state(qh, 0, 0, 4, 76, 10, 10, 1)
+        for a in (first, second):
+            g.step(a)
+            qh.qh_apply(s, a)
+        pos = g.position()
+        assert (s[0], s[1]) == (pos["H"], pos["V"])
+        assert bin(s[0] | s[1]).count("1") == 1
+        assert legal_list(qh, s) == g.actions()

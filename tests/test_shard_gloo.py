@@ -110,3 +110,82 @@ def test_trainer_gradient_allreduce_two_ranks():
     import numpy as np
     assert np.array_equal(res[0], res[1])
     assert np.isfinite(res[0]).all()
+
+
+def _pipeline_worker(rank, ws, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from alphazero_quoridor_b200.train import TrainPipeline
+        torch.set_num_threads(1)
+        torch.manual_seed(100 + rank)                         # DIFFERENT initial weights per rank: the constructor must broadcast
+
+        def fake_encode(rows):                                # CPU stand-in for the encode kernel (host logic under test)
+            bits = (rows[:, :2, None] >> torch.arange(41)) & 1                     # [B,2,41] -> 82 bits
+            x = bits.reshape(rows.shape[0], -1)[:, :81].float().reshape(-1, 1, 9, 9)
+            return x.expand(-1, 26, -1, -1).contiguous()
+        tp = TrainPipeline(use_gpu=False, encode_fn=fake_encode, seed=3)
+        tp.batch_size, tp.epochs = 16, 3
+        start = torch.cat([p.detach().reshape(-1) for p in tp.policy_value_net.policy_value_net.parameters()]).clone()
+        g = torch.Generator().manual_seed(50 + rank)          # different data on every rank
+
+        def feed(m):
+            st = torch.randint(0, 2 ** 62, (m, 3), generator=g, dtype=torch.int64)
+            pr = torch.rand((m, 140), generator=g)
+            tp.data_buffer.extend(st, pr / pr.sum(1, keepdim=True), torch.randint(0, 2, (m,), generator=g).float() * 2 - 1)
+        feed(40 if rank == 0 else 10)                         # rank 1 is NOT ready: nobody may update (or hang)
+        ready_first = tp.ready_to_update()
+        feed(30)
+        ready_second = tp.ready_to_update()
+        stats = []
+        for _ in range(3):
+            tp.policy_update()
+            stats.append((tp.last_stats["epochs"], tp.last_stats["kl"], tp.lr_multiplier))
+        flat = torch.cat([p.detach().reshape(-1) for p in tp.policy_value_net.policy_value_net.parameters()])
+        q.put((rank, ready_first, ready_second, stats, start.numpy(), flat.numpy()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_pipeline_collectives_are_rank_consistent():
+    """TrainPipeline on two ranks with different buffers, minibatches and initial seeds: the update gate, the KL early
+    stop and the learning-rate multiplier are decided collectively (same number of all-reduces on every rank -- a
+    rank-local decision here deadlocks), and the ranks start and end with identical weights."""
+    ws = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_pipeline_worker, args=(r, ws, port, q)) for r in range(ws)]
+    for p in procs:
+        p.start()
+    res = {r[0]: r[1:] for r in (q.get(timeout=280) for _ in range(ws))}
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    import numpy as np
+    assert res[0][0] is False and res[1][0] is False and res[0][1] is True and res[1][1] is True
+    assert res[0][2] == res[1][2]                              # epochs run, mean KL, lr multiplier: identical
+    assert np.array_equal(res[0][3], res[1][3])                # broadcast at construction
+    assert np.array_equal(res[0][4], res[1][4]) and np.isfinite(res[0][4]).all()
+    assert not np.array_equal(res[0][3], res[0][4])
+
+
+def test_replay_ring_matches_deque():
+    """ReplayBuffer == collections.deque(maxlen) of train.py:24 (order, eviction), sampling without replacement."""
+    from collections import deque
+    from alphazero_quoridor_b200.train import ReplayBuffer
+    rb, dq = ReplayBuffer(50, "cpu"), deque(maxlen=50)
+    g = torch.Generator().manual_seed(0)
+    k = 0
+    for m in (7, 30, 20, 1, 49, 120, 3):
+        st = torch.arange(k, k + m, dtype=torch.int64)[:, None].expand(-1, 3).contiguous()
+        rb.extend(st, torch.full((m, 140), 1.0 / 140), torch.ones(m))
+        dq.extend(range(k, k + m))
+        k += m
+        assert len(rb) == len(dq) and rb.ordered()[0][:, 0].tolist() == list(dq)
+        if len(rb) >= 10:
+            s, _, _ = rb.sample(10, generator=g)
+            vals = s[:, 0].tolist()
+            assert len(set(vals)) == 10 and set(vals) <= set(dq)
+    assert rb[0][0][0].item() == dq[0] and rb[0][2] == 1.0
