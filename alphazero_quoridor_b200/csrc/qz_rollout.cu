@@ -125,25 +125,40 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
 // Every lane tracks the same state redundantly (no broadcasts).  The draw sequence of qz_sample.cuh is made of
 // independent attempts, so the warp evaluates 32 of them at once: lane i decodes attempt 32*round + i.  A pawn
 // move is legal as it stands, hence only the wall attempts BEFORE the first pawn attempt of the round can matter;
-// exactly those are path-checked (one candidate per lane, both players' floods interleaved in that lane) and the
-// earliest legal attempt wins -- the same action the per-lane path would take.  In a stuck position ~4 % of the
-// attempts are pawn moves, so a ply costs about one flood-fill latency and ~25 path checks instead of the ~70 of
-// a full sweep, and a rollout occupies one warp: the pass is latency-bound, so its throughput is the number of
-// rollouts resident per SM.
-
+// exactly those need a verdict and the earliest legal attempt wins -- the same action the per-lane path would take.
+//
+// Legality memo.  Whether a wall keeps both paths (quoridor.py:463-477) is a pure function of (H, V, p1, p2), and a
+// stuck rollout plays hundreds of plies between two wall placements while the two pawns wander over a few dozen tile
+// pairs (host simulation: 270 wall-holding plies per wall configuration on 60 distinct pairs, 78 % of the plies
+// revisit a pair).  Per wall configuration ("epoch") the warp keeps a small table in shared memory, keyed by
+// (p1, p2): the candidates KNOWN legal and KNOWN blocking.  A ply first looks its pair up; a path check (two flood
+// fills, ~1000 instructions of latency for the whole warp) only runs when an attempt that can still win is unknown,
+// and then ALL 32 lanes check something: the lanes without an unknown attempt of their own take further unknown
+// candidates of the pair, so two or three flood rounds settle a pair for good.  Flood rounds per wall-holding ply:
+// 1.50 -> 0.49.  Everything else a ply needs is per-epoch data parked in shared memory: the byte-per-tile move table
+// (qz_tile_table, as in the pawn kernel), the corner masks, and the ordered wall part of the superset.
 #ifndef QZ_STUCK_THREADS
 #define QZ_STUCK_THREADS 32
 #endif
+#define QZ_MEMO_SLOTS 128              // per warp; 2-way: a pair lives in slot h or h+1
+
+struct QzStuckSmem {                   // one per warp
+    uint32_t ctx[QZ_CTX_WORDS];        // corner masks of the epoch's walls (words 0-11 = the four move masks)
+    uint32_t tile[QZ_TILE_TABLE_WORDS];   // byte t = move / corner info of tile t (qz_tile_table)
+    uint8_t wall_tab[128];             // the epoch's precheck-passing walls in superset order (H by ix, then V by ix)
+    uint32_t key[QZ_MEMO_SLOTS];       // epoch << 14 | p1 << 7 | p2 (0 = never used)
+    uint64_t kl_h[QZ_MEMO_SLOTS], kl_v[QZ_MEMO_SLOTS];   // known legal
+    uint64_t ki_h[QZ_MEMO_SLOTS], ki_v[QZ_MEMO_SLOTS];   // known blocking
+};
+
 __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
-    // the ordered superset S of the ply (qz_sample.cuh) as a byte table, built by the warp once per ply: decoding an
-    // attempt is then one shared-memory load instead of a k-th-set-bit search on every lane in every round
-    __shared__ uint8_t s_superset[QZ_STUCK_THREADS / 32][144];
-    // the corner masks of the current walls: a stuck rollout plays hundreds of plies between two wall placements,
-    // so they are parked here and reloaded (36 broadcast loads) instead of rebuilt (~250 instructions) every ply
-    __shared__ uint32_t s_ctx[QZ_STUCK_THREADS / 32][QZ_CTX_WORDS];
-    uint8_t *superset = s_superset[threadIdx.x >> 5];
-    uint32_t *ctx_words = s_ctx[threadIdx.x >> 5];
+    __shared__ QzStuckSmem s_all[QZ_STUCK_THREADS / 32];
+    QzStuckSmem &sm = s_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
+    const uint8_t *tile_bytes = reinterpret_cast<const uint8_t *>(sm.tile);
+    for (int i = lane; i < QZ_MEMO_SLOTS; i += 32) sm.key[i] = 0;
+    __syncwarp();
+    uint32_t epoch = 0;                                                  // bumped whenever the walls change
     for (;;) {
         unsigned long long k = 0;
         if (lane == 0) k = atomicAdd(a.counter + 4, 1ull);
@@ -155,67 +170,124 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs 
         const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, r)) + 2);
         int steps = (int)qz_ply(s.meta) - (int)qz_ply(m0);
         QzRng rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + r) : a.rid_base + (uint64_t)r);
-        uint64_t ctx_h = 0, ctx_v = 0;
-        bool ctx_parked = false;
+        uint64_t ep_h = 0, ep_v = 0, hc = 0, vc = 0;
+        int nh = 0, nv = 0;
+        bool ep_valid = false;
         for (;;) {
             if (qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0) break;
-            QzPawnCtx c;
-            if (ctx_parked && ctx_h == s.H && ctx_v == s.V) {
-                c = qz_ctx_load(ctx_words);
-            } else {
-                c = qz_ctx_build(s.H, s.V);
+            if (!(ep_valid && ep_h == s.H && ep_v == s.V)) {
+                // new wall configuration: park its masks, move table and wall candidates; old memo entries die with
+                // the epoch number
+                const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+                hc = qz_hcand(s.H, s.V); vc = qz_vcand(s.H, s.V);
+                nh = qz_popc64(hc); nv = qz_popc64(vc);
                 __syncwarp();
-                if (lane == 0) qz_ctx_store(c, ctx_words);
-                __syncwarp();
-                ctx_h = s.H; ctx_v = s.V; ctx_parked = true;
-            }
-            const uint32_t pawn = qz_mover_pawn_moves_ctx(c, s.meta);
-            const bool has_walls = qz_mover_walls(s.meta) > 0;
-            const uint64_t hc = has_walls ? qz_hcand(s.H, s.V) : 0ull, vc = has_walls ? qz_vcand(s.H, s.V) : 0ull;
-            const int npawn = qz_popc32(pawn), nh = qz_popc64(hc), nv = qz_popc64(vc);
-            const uint32_t M = (uint32_t)(npawn + nh + nv);
-            int act = -1;
-            if (M != 0 && !has_walls) {                                  // only pawn moves: attempt 0 is legal
-                act = qz_nth_bit64((uint64_t)pawn, (int)qz_mulhi32(qz_attempt_word(rng, (uint32_t)steps, 0), M));
-            } else if (M != 0) {
-                const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
-                __syncwarp();                                           // the previous ply's table is no longer read
+                if (lane == 0) { qz_ctx_store(c, sm.ctx); qz_tile_table(c, sm.tile, 1); }
 #pragma unroll
-                for (int q = 0; q < 5; q++) {
-                    const int act_q = lane + 32 * q;                    // actions 0..139 over five passes
-                    if (act_q < 12) {
-                        if ((pawn >> act_q) & 1u) superset[__popc(pawn & ((1u << act_q) - 1u))] = (uint8_t)act_q;
-                    } else if (act_q < 76) {
-                        const int ix = act_q - 12;
-                        if ((hc >> ix) & 1ull) superset[npawn + __popcll(hc & ((1ull << ix) - 1ull))] = (uint8_t)act_q;
-                    } else if (act_q < 140) {
-                        const int ix = act_q - 76;
-                        if ((vc >> ix) & 1ull) superset[npawn + nh + __popcll(vc & ((1ull << ix) - 1ull))] = (uint8_t)act_q;
-                    }
+                for (int q = 0; q < 2; q++) {
+                    const int ix = lane + 32 * q;
+                    if ((hc >> ix) & 1ull) sm.wall_tab[__popcll(hc & ((1ull << ix) - 1ull))] = (uint8_t)(12 + ix);
+                    if ((vc >> ix) & 1ull) sm.wall_tab[nh + __popcll(vc & ((1ull << ix) - 1ull))] = (uint8_t)(76 + ix);
                 }
                 __syncwarp();
-                uint64_t bad_h = 0, bad_v = 0;                          // walls already known to block (warp-uniform)
+                ep_h = s.H; ep_v = s.V; ep_valid = true;
+                epoch = (epoch + 1) & 0x3FFFFu;
+                if (epoch == 0) {                                        // tag wrapped: forget everything
+                    for (int i = lane; i < QZ_MEMO_SLOTS; i += 32) sm.key[i] = 0;
+                    __syncwarp();
+                    epoch = 1;
+                }
+            }
+            const int cur = qz_cur(s.meta), p1 = qz_p1(s.meta), p2 = qz_p2(s.meta);
+            const int L = cur == 1 ? p1 : p2, O = cur == 1 ? p2 : p1;
+            const uint32_t iL = tile_bytes[L], iO = tile_bytes[O];
+            uint32_t hO = 0;
+            if (qz_pawn_contact(iL, L, O) & 0xCu) {                      // east / west contact: the opponent's H corners matter
+                const uint32_t *hm = sm.ctx + 24 + (O >> 5);
+                const int sh = O & 31;
+                hO = ((hm[0] >> sh) & 1u) | (((hm[3] >> sh) & 1u) << 1) | (((hm[6] >> sh) & 1u) << 2) | (((hm[9] >> sh) & 1u) << 3);
+            }
+            const uint32_t pawn = qz_pawn_moves_info(iL, iO, hO, L, O, cur);     // quoridor.py:272-353
+            const int npawn = qz_popc32(pawn);
+            const bool has_walls = qz_mover_walls(s.meta) > 0;
+            int act = -1;
+            if (!has_walls) {                                            // only pawn moves: attempt 0 is legal
+                if (npawn) act = qz_nth_bit64((uint64_t)pawn, (int)qz_mulhi32(qz_attempt_word(rng, (uint32_t)steps, 0), (uint32_t)npawn));
+            } else if (npawn + nh + nv != 0) {
+                const uint32_t M = (uint32_t)(npawn + nh + nv);
+                // ---- memo lookup (all lanes compute the same slot; lane 0 writes) ----
+                const uint32_t key = (epoch << 14) | ((uint32_t)p1 << 7) | (uint32_t)p2;
+                int slot = (p1 * 5 + p2 * 11) & (QZ_MEMO_SLOTS - 1);
+                const int alt = (slot + 1) & (QZ_MEMO_SLOTS - 1);
+                const uint32_t k0 = sm.key[slot], k1 = sm.key[alt];
+                uint64_t klh = 0, klv = 0, kih = 0, kiv = 0;
+                if (k0 == key) {
+                    klh = sm.kl_h[slot]; klv = sm.kl_v[slot]; kih = sm.ki_h[slot]; kiv = sm.ki_v[slot];
+                } else if (k1 == key) {
+                    slot = alt;
+                    klh = sm.kl_h[slot]; klv = sm.kl_v[slot]; kih = sm.ki_h[slot]; kiv = sm.ki_v[slot];
+                } else {
+                    if ((k0 >> 14) == epoch && (k1 >> 14) != epoch) slot = alt;      // prefer a slot of a dead epoch
+                    __syncwarp();
+                    if (lane == 0) { sm.key[slot] = key; sm.kl_h[slot] = 0; sm.kl_v[slot] = 0; sm.ki_h[slot] = 0; sm.ki_v[slot] = 0; }
+                }
+                __syncwarp();
+                bool dirty = false, prepared = false;
+                QzSweep w;
                 for (uint32_t round = 0; act < 0; round++) {
                     const uint32_t word = qz_attempt_word(rng, (uint32_t)steps, round * 32 + lane);
-                    const int cand = superset[qz_mulhi32(word, M)];
+                    const int kk = (int)qz_mulhi32(word, M);
+                    const int cand = kk < npawn ? qz_nth_bit64((uint64_t)pawn, kk) : (int)sm.wall_tab[kk - npawn];
                     const unsigned pawn_lanes = __ballot_sync(QZ_FULL_MASK, cand < 12);
                     const int first_pawn = pawn_lanes ? __ffs(pawn_lanes) - 1 : 32;
-                    bool ok = false;
-                    if (lane < first_pawn) {                             // a wall attempt that can still win the draw
-                        const bool vert = cand >= 76;
-                        const int ix = vert ? cand - 76 : cand - 12;
-                        if (!(((vert ? bad_v : bad_h) >> ix) & 1ull)) ok = qz_wall_keeps_paths(w, ix, vert);
+                    const bool vert = cand >= 76;
+                    const int ix = vert ? cand - 76 : cand - 12;        // garbage on pawn lanes, masked by `mine`
+                    const uint64_t bit = 1ull << (ix & 63);
+                    const bool mine = lane < first_pawn;                 // a wall attempt that can still win the draw
+                    const unsigned known_ok = __ballot_sync(QZ_FULL_MASK, mine && ((vert ? klv : klh) & bit));
+                    const int limit = known_ok ? __ffs(known_ok) - 1 : first_pawn;   // attempts after a sure winner are moot
+                    const bool need = lane < limit && !((vert ? kiv : kih) & bit);  // unknown and still able to win
+                    const unsigned need_lanes = __ballot_sync(QZ_FULL_MASK, need);
+                    if (need_lanes) {
+                        // one flood round for the whole warp: the `need` lanes check their own attempt, every other
+                        // lane takes one more unknown candidate of this pair
+                        uint64_t uh = hc & ~(klh | kih), uv = vc & ~(klv | kiv);
+                        uh &= ~qz_warp_or64(need && !vert ? bit : 0ull);
+                        uv &= ~qz_warp_or64(need && vert ? bit : 0ull);
+                        const int nuh = qz_popc64(uh), nu = nuh + qz_popc64(uv);
+                        const int rank = __popc(~need_lanes & ((1u << lane) - 1u));
+                        bool chk = need, cvert = vert;
+                        int cix = ix & 63;
+                        if (!need && rank < nu) {
+                            chk = true;
+                            cvert = rank >= nuh;
+                            cix = cvert ? qz_nth_bit64(uv, rank - nuh) : qz_nth_bit64(uh, rank);
+                        }
+                        if (!prepared) {
+                            w.H = s.H; w.V = s.V; w.p1 = p1; w.p2 = p2;
+                            w.dirs.n = bb_make(sm.ctx[0], sm.ctx[1], sm.ctx[2]); w.dirs.s = bb_make(sm.ctx[3], sm.ctx[4], sm.ctx[5]);
+                            w.dirs.e = bb_make(sm.ctx[6], sm.ctx[7], sm.ctx[8]); w.dirs.w = bb_make(sm.ctx[9], sm.ctx[10], sm.ctx[11]);
+                            prepared = true;
+                        }
+                        const bool ok = chk && qz_wall_keeps_paths(w, cix, cvert);
+                        const uint64_t cbit = 1ull << cix;
+                        klh |= qz_warp_or64(chk && ok && !cvert ? cbit : 0ull);
+                        klv |= qz_warp_or64(chk && ok && cvert ? cbit : 0ull);
+                        kih |= qz_warp_or64(chk && !ok && !cvert ? cbit : 0ull);
+                        kiv |= qz_warp_or64(chk && !ok && cvert ? cbit : 0ull);
+                        dirty = true;
                     }
-                    const unsigned ok_lanes = __ballot_sync(QZ_FULL_MASK, ok);
+                    const unsigned ok_lanes = __ballot_sync(QZ_FULL_MASK, mine && ((vert ? klv : klh) & bit));
                     const int winner = ok_lanes ? __ffs(ok_lanes) - 1 : first_pawn;      // earliest legal attempt
                     if (winner < 32) { act = __shfl_sync(QZ_FULL_MASK, cand, winner); break; }
-                    // all 32 attempts were blocking walls: remember them; with no pawn move at all, stop once every
-                    // candidate is known to block (stalemate; the reference would return [] and crash)
-                    const bool vert = cand >= 76;
-                    const int ix = vert ? cand - 76 : cand - 12;
-                    bad_h |= qz_warp_or64(vert ? 0ull : 1ull << ix);
-                    bad_v |= qz_warp_or64(vert ? 1ull << ix : 0ull);
-                    if (npawn == 0 && bad_h == hc && bad_v == vc) break;
+                    // all 32 attempts were blocking walls; with no pawn move at all, stop once every candidate is known
+                    // to block (stalemate; the reference would return [] and crash)
+                    if (npawn == 0 && kih == hc && kiv == vc) break;
+                }
+                if (dirty) {
+                    __syncwarp();
+                    if (lane == 0) { sm.kl_h[slot] = klh; sm.kl_v[slot] = klv; sm.ki_h[slot] = kih; sm.ki_v[slot] = kiv; }
+                    __syncwarp();
                 }
             }
             if (act < 0) { s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40; break; }

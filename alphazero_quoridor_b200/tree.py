@@ -21,6 +21,7 @@ from .rollout import rollout as _rollout
 
 LEAF_TERMINAL, LEAF_DEPTH_OVERFLOW, LEAF_ARENA_OVERFLOW, LEAF_DUPLICATE, LEAF_INACTIVE, LEAF_PENDING = 1, 2, 4, 8, 16, 32
 MAX_CHILDREN = 140
+MAX_K_NONUNIFORM = 8                   # leaves per game per wave allowed under non-uniform priors (see BatchedMCTS)
 PLAYOUT_BITS = 24                      # rollout stream id = game_id << 24 | playout counter (mod 2^24)
 PLAYOUT_MASK = (1 << PLAYOUT_BITS) - 1
 
@@ -164,7 +165,7 @@ class NetEvaluator:
 class BatchedMCTS:
     def __init__(self, n_games, evaluator, c_puct=5, n_playout=100, leaves_per_game=1, node_cap=None,
                  max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None, defer_depth=0,
-                 defer_until_drain=False):
+                 defer_until_drain=False, allow_large_k=False):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda")
@@ -176,6 +177,13 @@ class BatchedMCTS:
         self.n_playout = int(n_playout)
         self.evaluator = evaluator
         self.uniform_prior = bool(getattr(evaluator, "uniform_prior", False))
+        # Virtual loss is only a mild perturbation while the leaves of a wave spread over many near-equal children.
+        # Under uniform priors (pure MCTS) K = 64 moves the root visit distribution by a total-variation distance of
+        # ~1e-4; under sharply non-uniform priors K = 64 reaches 0.19.  K is therefore capped for
+        # evaluators with non-uniform priors unless the caller insists (tests/test_bench_parity.py holds the bounds).
+        if not self.uniform_prior and self.K > MAX_K_NONUNIFORM and not allow_large_k:
+            raise ValueError("leaves_per_game=%d with a non-uniform-prior evaluator exceeds the parity-tested cap of %d "
+                             "(pass allow_large_k=True to override)" % (self.K, MAX_K_NONUNIFORM))
         self.fix_terminal_sign = bool(fix_terminal_sign)
         self.max_depth = int(max_depth)
         if node_cap is None:
