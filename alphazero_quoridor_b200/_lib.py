@@ -11,7 +11,7 @@ import torch
 _PKG = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(_PKG, "libqzb200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 N_ACTIONS = 140
 STATE_ELEMS = 26 * 9 * 9
 DTYPE_CODE = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
@@ -30,6 +30,7 @@ SIGNATURES = {
     "qz_version": (C.c_int, []),
     "qz_last_error_string": (C.c_char_p, []),
     "qz_device_sm_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "qz_stream_check": (C.c_int, [_vp]),
     "qz_env_reset": (C.c_int, [_vp, _i64, _vp]),
     "qz_env_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "qz_env_legal_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
@@ -42,11 +43,12 @@ SIGNATURES = {
     "qz_rollout_finish": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "qz_mcts_backup_pending": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "qz_mcts_init": (C.c_int, [_vp, _vp, _vp, _vp]),
-    "qz_mcts_select": (C.c_int, [_vp, _f64, C.c_int, C.c_int, _vp]),
-    "qz_mcts_expand_backup": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "qz_mcts_select": (C.c_int, [_vp, _f64, C.c_int, C.c_int, _vp, _vp]),
+    "qz_mcts_expand_backup": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f64, C.c_int, _vp, _vp]),
     "qz_mcts_root_stats": (C.c_int, [_vp, _f64, _vp, _vp, _vp, _vp, _vp]),
     "qz_mcts_choose": (C.c_int, [_vp, C.c_int, _f64, _f64, _f64, _u64, _vp, _vp, _vp]),
-    "qz_mcts_reroot": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp]),
+    "qz_mcts_reroot": (C.c_int, [_vp, _vp, _vp, C.c_int, _vp, _vp]),
+    "qz_mcts_node_children": (C.c_int, [_vp, _i64, _i32, _vp, _vp, _vp]),
     "qz_stub_eval": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _i64, _vp]),
 }
 
@@ -79,7 +81,7 @@ LAUNCHES = 0      # kernels of ours launched through the C ABI (bench.py reports
 
 # kernels launched by one successful call of each entry point; the rollout entry points pass their own count
 # (wall + stuck + qz_rollout_pawn_passes(limit) pawn passes, see rollout.py)
-KERNELS_PER_CALL = {"qz_env_random_play": 2}
+KERNELS_PER_CALL = {"qz_env_random_play": 2, "qz_stream_check": 0}
 
 
 def check(rc, what="", launches=None):

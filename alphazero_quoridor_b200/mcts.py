@@ -88,41 +88,46 @@ class TreeNode(object):
     """Read-only view of one node of the device tree with the reference's TreeNode surface (mcts.py:12-80):
     `_n_visits`, `_Q`, `_P`, `_u`, `_children` (dict action -> TreeNode, in insertion order), `_parent`,
     `is_leaf()`, `is_root()`, `get_value(c_puct)`.  The statistics live in the flat device arrays of
-    tree.BatchedMCTS; this object copies what it is asked for.  Mutation (expand/update/select) happens in the
-    kernels, so those methods are not offered here."""
+    tree.BatchedMCTS; this object copies what it is asked for (qz_mcts_node_children).  The device tree gives a child
+    its slot when it is first visited; a child without one is the reference's freshly expanded child (0 visits, Q 0, its
+    prior, no children) and is shown as such.  Mutation (expand/update/select) happens in the kernels, so those methods
+    are not offered here."""
 
-    def __init__(self, engine, game_index, node, parent=None, uniform_prior=False):
+    def __init__(self, engine, game_index, node, parent=None, uniform_prior=False, info=None):
         self._engine, self._g, self._node, self._parent = engine, game_index, int(node), parent
         self._uniform = uniform_prior
+        self._info = info                  # dict(visits, q, prior) for a child read with its parent; None = read on demand
+        self._kids = None
 
-    def _at(self, name):
-        a = self._engine.arena
-        return getattr(a, name)[self._g * self._engine.node_cap + self._node].item()
+    def _read(self):
+        if self._kids is None and self._node >= 0:
+            kids, me = self._engine.node_children(self._g, self._node)
+            self._kids = kids
+            if self._info is None:
+                self._info = me
+        return self._info or dict(visits=0, q=0.0, prior=0.0)
 
     @property
     def _n_visits(self):
-        return int(self._at("visits"))
+        return int((self._info or self._read())["visits"])
 
     @property
     def _Q(self):
-        return float(self._at("q"))
+        return float((self._info or self._read())["q"])
 
     @property
     def _P(self):
         if self._uniform and self._parent is not None:
             return 1.0 / len(self._parent._children)
-        return float(np.float32(self._at("prior")))
+        return float(np.float32((self._info or self._read())["prior"]))
 
     @property
     def _children(self):
-        eng = self._engine
-        base = int(self._at("child_base"))
-        if base < 0:
+        if self._node < 0:
             return {}
-        o = self._g * eng.node_cap
-        nc = (int(self._at("node_meta")) >> 8) & 0xFF
-        acts = eng.arena.node_meta[o + base:o + base + nc].cpu().numpy()
-        return {int(a) & 0xFF: TreeNode(eng, self._g, base + j, self, self._uniform) for j, a in enumerate(acts)}
+        self._read()
+        return {k["action"]: TreeNode(self._engine, self._g, k["slot"], self, self._uniform,
+                                      info=dict(visits=k["visits"], q=k["q"], prior=k["prior"])) for k in self._kids}
 
     @property
     def _u(self):
@@ -133,11 +138,11 @@ class TreeNode(object):
         if self._uniform:
             cp = c_puct * self._P
         else:
-            cp = float(np.float32(c_puct) * np.float32(self._at("prior")))
+            cp = float(np.float32(c_puct) * np.float32((self._info or self._read())["prior"]))
         return self._Q + cp * np.sqrt(self._parent._n_visits) / (1 + self._n_visits)
 
     def is_leaf(self):
-        return int(self._at("child_base")) < 0
+        return len(self._children) == 0
 
     def is_root(self):
         return self._parent is None
@@ -165,7 +170,8 @@ class MCTS(object):
     def _root(self):
         """The root as a reference-style TreeNode view (mcts.py:97)."""
         self._engine.drain()
-        return TreeNode(self._engine, 0, int(self._engine.arena.root[0].item()))
+        return TreeNode(self._engine, 0, int(self._engine.arena.root[0].item()),
+                        uniform_prior=self._engine.uniform_prior)
 
     def _playout(self, game):
         """mcts.py:103-127: ONE playout from `game` (the reference mutates the game copy it is given; here the
@@ -185,32 +191,13 @@ class MCTS(object):
 
     def _root_children(self, visits140=None):
         """(acts in child order, visits) of the root."""
-        eng = self._engine
-        a = eng.arena
-        root = int(a.root[0].item())
-        base = int(a.child_base[root].item())
-        if base < 0:
-            return [], []
-        nc = (int(a.node_meta[root].item()) >> 8) & 0xFF
-        meta = a.node_meta[base:base + nc].cpu().numpy()
-        acts = [int(x) & 0xFF for x in meta]
-        visits = [int(x) for x in a.visits[base:base + nc].cpu().numpy()]
-        return acts, visits
+        kids, _ = self._engine.node_children(0, int(self._engine.arena.root[0].item()))
+        return [k["action"] for k in kids], [k["visits"] for k in kids]
 
     def root_children_stats(self):
         """(acts, visits, Q) of the root's children plus (root visits, root Q) -- for tests / inspection."""
-        eng = self._engine
-        a = eng.arena
-        root = int(a.root[0].item())
-        base = int(a.child_base[root].item())
-        rn, rq = int(a.visits[root].item()), float(a.q[root].item())
-        if base < 0:
-            return [], [], [], rn, rq
-        nc = (int(a.node_meta[root].item()) >> 8) & 0xFF
-        acts = [int(x) & 0xFF for x in a.node_meta[base:base + nc].cpu().numpy()]
-        visits = [int(x) for x in a.visits[base:base + nc].cpu().numpy()]
-        qs = [float(x) for x in a.q[base:base + nc].cpu().numpy()]
-        return acts, visits, qs, rn, rq
+        kids, me = self._engine.node_children(0, int(self._engine.arena.root[0].item()))
+        return ([k["action"] for k in kids], [k["visits"] for k in kids], [k["q"] for k in kids], me["visits"], me["q"])
 
     def update_with_move(self, last_move):
         """mcts.py:146-151"""

@@ -70,6 +70,35 @@ def mirror_samples(states, probs):
     return out, probs[:, MIRROR_ACTION.to(probs.device)]
 
 
+def play_match(engine_a, engine_b, max_plies=300):
+    """Arena: two `BatchedMCTS` engines (same number of games, fresh trees every move) play n games against each other
+    side by side on the device; A moves first in even games, second in odd ones; every move is the most visited one
+    (mcts.py:185 at temp -> 0 / pure_mcts.py:115).  Returns wins / ties and A's score ratio (ties count half), as the
+    reference's commented-out policy_evaluate would (train.py:30-31,108)."""
+    n, dev = engine_a.n, engine_a.device
+    assert engine_b.n == n
+    env = BatchedQuoridor(n, device=dev)
+    a_color = (torch.arange(n, device=dev) % 2) + 1                         # 1: A moves first, 2: second
+    plies = 0
+    for plies in range(max_plies):
+        meta = env.states[:, 2]
+        if bool((((meta >> 40) & 1) == 1).all()):
+            break
+        engine_a.reset(env.states)
+        engine_a.search()
+        engine_b.reset(env.states)
+        engine_b.search()
+        mover = (meta >> 32) & 0xFF
+        moves = torch.where(mover == a_color, engine_a.choose(mode=0), engine_b.choose(mode=0))
+        env.step(moves)                                                       # finished games / stalemated movers stay put
+    meta = env.states[:, 2]
+    winner = torch.where(((meta >> 40) & 1) == 1, (meta >> 41) & 3, torch.zeros_like(meta))
+    wins_a = int((winner == a_color).sum().item())
+    ties = int((winner == 0).sum().item())
+    return {"games": n, "wins_a": wins_a, "wins_b": n - wins_a - ties, "ties": ties, "plies": plies + 1,
+            "win_ratio_a": (wins_a + 0.5 * ties) / n}
+
+
 class ReplayBuffer(object):
     """`deque(maxlen=buffer_size)` of train.py:24 as a ring of device tensors: the 24-byte game state (re-encoded by
     the encode kernel when a minibatch is drawn, instead of the float64 [26,9,9] array of quoridor.py:589), the 140
@@ -290,24 +319,9 @@ class TrainPipeline(object):
                          leaves_per_game=self.leaves_per_game, reuse_tree=False, fix_terminal_sign=True, device=dev)
         pure = BatchedMCTS(n_games, RolloutEvaluator(seed=seed), c_puct=5, n_playout=self.pure_mcts_playout_num,
                            leaves_per_game=16, reuse_tree=False, fix_terminal_sign=True, device=dev)
-        env = BatchedQuoridor(n_games, device=dev)
-        az_color = (torch.arange(n_games, device=dev) % 2) + 1               # 1: net moves first, 2: second
-        for ply in range(max_plies):
-            meta = env.states[:, 2]
-            if bool((((meta >> 40) & 1) == 1).all()):
-                break
-            az.reset(env.states)
-            az.search()
-            pure.reset(env.states)
-            pure.search()
-            mover = (meta >> 32) & 0xFF
-            moves = torch.where(mover == az_color, az.choose(mode=0), pure.choose(mode=0))
-            env.step(moves)
-        meta = env.states[:, 2]
-        winner = (meta >> 41) & 3
-        wins = (winner == az_color).sum().item()
-        ties = (winner == 0).sum().item()
-        return (wins + 0.5 * ties) / n_games
+        res = play_match(az, pure, max_plies=max_plies)
+        self.last_match = res
+        return res["win_ratio_a"]
 
     def run(self):
         """train.py:94-111"""

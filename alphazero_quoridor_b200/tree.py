@@ -21,6 +21,7 @@ from .rollout import rollout as _rollout
 
 LEAF_TERMINAL, LEAF_DEPTH_OVERFLOW, LEAF_ARENA_OVERFLOW, LEAF_DUPLICATE, LEAF_INACTIVE, LEAF_PENDING = 1, 2, 4, 8, 16, 32
 MAX_CHILDREN = 140
+SLOTS_PER_PLAYOUT = 12                 # default arena slots per playout kept (see BatchedMCTS.__init__)
 MAX_K_NONUNIFORM = 8                   # leaves per game per wave allowed under non-uniform priors (see BatchedMCTS)
 PLAYOUT_BITS = 24                      # rollout stream id = game_id << 24 | playout counter (mod 2^24)
 PLAYOUT_MASK = (1 << PLAYOUT_BITS) - 1
@@ -29,18 +30,22 @@ PLAYOUT_MASK = (1 << PLAYOUT_BITS) - 1
 class QzTree(C.Structure):
     """struct qz_tree of include/qzb200.h."""
     _fields_ = [("n_games", C.c_int64), ("node_cap", C.c_int32), ("max_depth", C.c_int32),
-                ("leaves_per_game", C.c_int32), ("reserved", C.c_int32),
+                ("leaves_per_game", C.c_int32), ("pool_cap", C.c_int32),
                 ("prior", C.c_void_p), ("visits", C.c_void_p), ("q", C.c_void_p), ("child_base", C.c_void_p),
                 ("node_meta", C.c_void_p), ("root", C.c_void_p), ("n_nodes", C.c_void_p),
                 ("root_state", C.c_void_p), ("leaf_node", C.c_void_p), ("leaf_state", C.c_void_p),
-                ("path", C.c_void_p), ("path_len", C.c_void_p), ("leaf_flags", C.c_void_p)]
+                ("path", C.c_void_p), ("path_len", C.c_void_p), ("leaf_flags", C.c_void_p),
+                ("prior_pool", C.c_void_p), ("n_pool", C.c_void_p)]
 
 
 class _Arena:
     """One set of node arrays for n games (a second one is the re-root compaction target)."""
 
-    def __init__(self, n, cap, dev):
+    def __init__(self, n, cap, dev, pool_cap=0):
         tot = n * cap
+        # stored (non-uniform) priors: one row of 140 per expanded node (children get their slot when first visited)
+        self.prior_pool = torch.empty(n * pool_cap * 140, dtype=torch.float32, device=dev) if pool_cap else None
+        self.n_pool = torch.zeros(n, dtype=torch.int32, device=dev) if pool_cap else None
         self.prior = torch.empty(tot, dtype=torch.float32, device=dev)
         self.visits = torch.empty(tot, dtype=torch.int32, device=dev)
         self.q = torch.empty(tot, dtype=torch.float64, device=dev)
@@ -186,14 +191,19 @@ class BatchedMCTS:
                              "(pass allow_large_k=True to override)" % (self.K, MAX_K_NONUNIFORM))
         self.fix_terminal_sign = bool(fix_terminal_sign)
         self.max_depth = int(max_depth)
+        # playouts whose nodes one arena may have to hold: one search, or two with tree reuse (the kept subtree of the
+        # previous move plus this move's playouts; a sharply peaked search can keep more -- the overflow counter tells)
+        kept = self.n_playout * (2 if reuse_tree else 1) + self.K
         if node_cap is None:
-            # an expansion adds at most 6 pawn moves + 128 walls; 140 = the action space (headroom for re-rooted subtrees)
-            node_cap = 1 + (self.n_playout * (2 if reuse_tree else 1) + self.K) * MAX_CHILDREN
+            # lazy children: a playout adds at most one child slot (<= 4 amortised with block doubling and the copies
+            # it leaves behind) and one block (3 header + 4 child slots); the root's block holds all <= 140 children
+            node_cap = 160 + kept * SLOTS_PER_PLAYOUT
         self.node_cap = int(node_cap)
+        self.pool_cap = 0 if self.uniform_prior else kept + 1
         dev = self.device
-        self.arenas = [_Arena(self.n, self.node_cap, dev)]
+        self.arenas = [_Arena(self.n, self.node_cap, dev, self.pool_cap)]
         if reuse_tree:
-            self.arenas.append(_Arena(self.n, self.node_cap, dev))
+            self.arenas.append(_Arena(self.n, self.node_cap, dev, self.pool_cap))
         self.cur = 0
         m = self.n * self.K
         # deferred evaluation (stuck rollouts finished on a side stream while later waves run): wave w's owed
@@ -241,9 +251,12 @@ class BatchedMCTS:
 
     def _make_struct(self, a, ls):
         t = QzTree()
-        t.n_games, t.node_cap, t.max_depth, t.leaves_per_game, t.reserved = self.n, self.node_cap, self.max_depth, self.K, 0
+        t.n_games, t.node_cap, t.max_depth, t.leaves_per_game, t.pool_cap = (self.n, self.node_cap, self.max_depth, self.K,
+                                                                              self.pool_cap)
         for name in ("prior", "visits", "q", "child_base", "node_meta", "root", "n_nodes", "root_state"):
             setattr(t, name, getattr(a, name).data_ptr())
+        t.prior_pool = a.prior_pool.data_ptr() if a.prior_pool is not None else None
+        t.n_pool = a.n_pool.data_ptr() if a.n_pool is not None else None
         for name in ("leaf_node", "leaf_state", "path", "path_len", "leaf_flags"):
             setattr(t, name, getattr(ls, name).data_ptr())
         return t
@@ -318,8 +331,27 @@ class BatchedMCTS:
                                                    int(self.fix_terminal_sign), self._stream()), "qz_mcts_backup_pending")
         ls.owed = None
 
-    def drain(self):
+    def check_device(self):
+        """Wait for this engine's stream and raise QzError if any kernel faulted since the last check (launch return
+        codes cannot see asynchronous faults; see qz_stream_check in include/qzb200.h)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qz_stream_check(self._stream()), "qz_stream_check")
+
+    def counters(self):
+        """Structured counters of this engine (synchronises): what a per-wave log line needs."""
+        out = {"games": self.n, "leaves_per_game": self.K, "waves": self.wave_index, "playouts_per_game": self.total_playouts,
+               "arena_overflows": self.overflow_count(), "nodes_in_use_mean": float(self.arena.n_nodes.double().mean().item()),
+               "node_cap": self.node_cap, "launches": _lib.LAUNCHES}
+        if hasattr(self.evaluator, "plies_played"):
+            out["rollout_plies"] = self.evaluator.plies_played()
+        if self.count_tree_steps:
+            out["tree_steps"] = int(self.tree_steps.item())
+        return out
+
+    def drain(self, check=False):
         """Settle every deferred wave (before reading statistics, choosing a move or re-rooting)."""
+        if check:
+            self.check_device()
         if self.defer_depth >= 2:
             with torch.cuda.device(self.device):
                 order = [(self.cur_set + 1 + i) % len(self.sets) for i in range(len(self.sets))]     # oldest first
@@ -339,8 +371,8 @@ class BatchedMCTS:
                 self.cur_set = self.wave_index % len(self.sets)
                 self._settle(self.cur_set)          # the wave that used this leaf set defer_depth waves ago
             ls = self.sets[self.cur_set]
-            _lib.check(self.lib.qz_mcts_select(C.byref(self.tree), self.c_puct, int(self.uniform_prior), k, st),
-                       "qz_mcts_select")
+            _lib.check(self.lib.qz_mcts_select(C.byref(self.tree), self.c_puct, int(self.uniform_prior), k,
+                                               _lib.ptr(self.overflow), st), "qz_mcts_select")
             m = self.n * self.K
             if self.count_tree_steps:
                 self.tree_steps += (ls.path_len.clamp(min=1) - 1).sum()
@@ -361,7 +393,7 @@ class BatchedMCTS:
             _lib.check(self.lib.qz_mcts_expand_backup(
                 C.byref(self.tree), _lib.ptr(ls.leaf_mask), _lib.ptr(ev.get("priors")),
                 _lib.ptr(ev.get("value_f32")), _lib.ptr(ev.get("value_f64")), _lib.ptr(ev.get("value_i8")),
-                int(self.fix_terminal_sign), _lib.ptr(self.overflow), st), "qz_mcts_expand_backup")
+                self.c_puct, int(self.fix_terminal_sign), _lib.ptr(self.overflow), st), "qz_mcts_expand_backup")
             if defer and not self.defer_until_drain:
                 # finish the stuck rollouts of this wave on the side stream while the next waves run
                 self._launch_finish(self.cur_set)
@@ -415,8 +447,8 @@ class BatchedMCTS:
         with torch.cuda.device(self.device):
             if keep_subtree and len(self.arenas) == 2:
                 src, dst = self._structs[self.cur][self.cur_set], self._structs[1 - self.cur][self.cur_set]
-                _lib.check(self.lib.qz_mcts_reroot(C.byref(src), C.byref(dst), _lib.ptr(moves), 1, self._stream()),
-                           "qz_mcts_reroot")
+                _lib.check(self.lib.qz_mcts_reroot(C.byref(src), C.byref(dst), _lib.ptr(moves), 1, _lib.ptr(self.overflow),
+                                                   self._stream()), "qz_mcts_reroot")
                 self.cur = 1 - self.cur
             else:
                 st = self._stream()
@@ -427,3 +459,18 @@ class BatchedMCTS:
 
     def overflow_count(self):
         return int(self.overflow.item())
+
+    def node_children(self, game, node):
+        """`node._children` of slot `node` of game `game` (mcts.py:19-25) in actions() order, children that never got a
+        slot included: list of dicts(action, slot, visits, q, prior, inflight), plus the node's own (visits, q, prior,
+        resolved slot).  One tiny kernel + one copy: for inspection and the reference-style TreeNode view."""
+        self.drain()
+        out_i = torch.zeros(4 + 4 * 140, dtype=torch.int32, device=self.device)
+        out_d = torch.zeros(2 + 2 * 140, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.qz_mcts_node_children(C.byref(self.tree), int(game), int(node), _lib.ptr(out_i),
+                                                      _lib.ptr(out_d), self._stream()), "qz_mcts_node_children")
+        oi, od = out_i.cpu().numpy(), out_d.cpu().numpy()
+        kids = [dict(action=int(oi[4 + 4 * r]), slot=int(oi[5 + 4 * r]), visits=int(oi[6 + 4 * r]), inflight=int(oi[7 + 4 * r]),
+                     q=float(od[2 + 2 * r]), prior=float(od[3 + 2 * r])) for r in range(int(oi[0]))]
+        return kids, dict(visits=int(oi[1]), slot=int(oi[2]), q=float(od[0]), prior=float(od[1]))

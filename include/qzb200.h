@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define QZ_ABI_VERSION 1
+#define QZ_ABI_VERSION 2
 
 #define QZ_N_ACTIONS 140
 #define QZ_N_PLANES 26
@@ -73,6 +73,13 @@ const char *qz_last_error_string(void);
 
 /* Number of SMs of the current device (grid sizing for callers); negative/positive error as above. */
 int qz_device_sm_count(int *out_sm_count);
+
+/* Kernel launches are asynchronous: the int every entry point returns only reports argument and LAUNCH errors.  A fault
+ * inside a kernel (an illegal address in a persistent kernel, say) would otherwise surface at some later, unrelated
+ * call.  qz_stream_check waits for `stream` and returns the device's error state: 0, or the positive cudaError_t with
+ * its text in qz_last_error_string().  Callers place it where they synchronise anyway (BatchedMCTS.drain(check=True),
+ * the tests); with the environment variable QZ_SYNC_CHECK set, EVERY entry point does it after launching (debugging). */
+int qz_stream_check(void *stream);
 
 /* Quoridor.__init__/reset (quoridor.py:9-56): n initial states. */
 int qz_env_reset(qz_state *states, int64_t n, void *stream);
@@ -167,20 +174,28 @@ int qz_rollout_finish(const qz_state *states, int64_t n_states, const int32_t *s
  * Batched PUCT MCTS (mcts.py, pure_mcts.py).  n_games trees live in flat, caller-owned device arrays.
  *
  * qz_tree is a HOST struct of device pointers and sizes, passed by pointer and copied by the call.
- * Game g owns node slots [g*node_cap, (g+1)*node_cap); a node's children are contiguous and stored in
- * the reference's actions() order (so mcts.py:42's first-max tie-break is "lowest child index").
- *   per node : prior f32 (TreeNode._P), visits i32 (_n_visits), q f64 (_Q), child_base i32 (-1 = is_leaf()),
- *              node_meta u32 = action | n_children << 8 | in-flight (virtual loss) count << 16
- *   per game : root (node index, always 0 after init/reroot), n_nodes (bump allocator), root_state
- *   per leaf : (n_games * leaves_per_game entries, refilled by every select) leaf_node, leaf_state,
- *              path[max_depth] + path_len (root..leaf node indices), leaf_flags (QZ_LEAF_*)
+ * Game g owns the slots [g*node_cap, (g+1)*node_cap) of five arrays.  Children are created LAZILY: TreeNode.expand
+ * (mcts.py:27-35) writes a 3-slot block header (the node's 140-bit legal mask, children in existence, capacity, legal
+ * count) followed by room for child slots, and a child gets its slot the first time the descent picks it -- a child
+ * never visited has Q = 0 and n = 0, so the reference's first-max over all children (mcts.py:42) is reproduced exactly
+ * from the existing children plus ONE candidate (the unvisited child with the largest c_puct*P, lowest actions() rank
+ * on ties; with uniform priors simply the next action in actions() order).  See csrc/qz_mcts.cu for the encoding.
+ *   child slot : prior f32 (TreeNode._P), visits i32 (_n_visits), q f64 (_Q), child_base i32 (-1 = is_leaf(), >= 0 = its
+ *                block, <= -2 = moved to slot -2 - x), node_meta u32 = action | actions() rank << 8 | in-flight << 16
+ *   per game   : root (slot index, always 0 after init/reroot), n_nodes (bump allocator), root_state;
+ *                with stored (non-uniform) priors: prior_pool rows of 140 f32, one per expanded node, n_pool rows used
+ *   per leaf   : (n_games * leaves_per_game entries, refilled by every select) leaf_node, leaf_state,
+ *                path[max_depth] + path_len (root..leaf slot indices), leaf_flags (QZ_LEAF_*)
+ * Sizing: a playout adds at most one child slot (amortised <= 4 with block doubling) and one block (3 + 4 slots), the
+ * root's block has room for all its children: node_cap >= 160 + 12 * playouts kept per game is ample
+ * (~0.3 MB per game for 1000 playouts; the eager layout of ABI 1 needed 3.4 MB).
  */
 typedef struct qz_tree {
     int64_t n_games;
     int32_t node_cap;
     int32_t max_depth;
     int32_t leaves_per_game;
-    int32_t reserved;
+    int32_t pool_cap;           /* rows of prior_pool per game (0 = uniform priors only) */
     float *prior;
     int32_t *visits;
     double *q;
@@ -194,6 +209,8 @@ typedef struct qz_tree {
     int32_t *path;
     int32_t *path_len;
     uint8_t *leaf_flags;
+    float *prior_pool;          /* [n_games * pool_cap * 140] or NULL */
+    int32_t *n_pool;            /* [n_games] or NULL */
 } qz_tree;
 
 #define QZ_LEAF_TERMINAL 0x01       /* the game is over at the leaf (never sent to the evaluator's result) */
@@ -211,8 +228,10 @@ int qz_mcts_init(const qz_tree *tree, const qz_state *root_states, const uint8_t
  * leaves_per_game) descents from the root by first-max of Q + c_puct*P*sqrt(N_parent)/(1+n) (TreeNode.select /
  * get_value, mcts.py:37-42,64-70), replaying Quoridor.step from root_state.  Fills the per-leaf arrays.
  * uniform_prior != 0: priors are 1/len(children) in float64 (pure_mcts.py:13-16) instead of the stored f32.
- * With k_leaves > 1 later descents see a virtual loss on earlier paths (deviation; k_leaves = 1 is exact). */
-int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, void *stream);
+ * With k_leaves > 1 later descents see a virtual loss on earlier paths (deviation; k_leaves = 1 is exact).
+ * A child picked for the first time gets its slot here (overflow_count, nullable, counts the slots that did not fit). */
+int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, int32_t *overflow_count,
+                   void *stream);
 
 /* The rest of MCTS._playout (mcts.py:117-127): for every leaf of the last select, unless terminal, expand
  * with (action, prior) over the legal actions in actions() order (TreeNode.expand, mcts.py:27-35; priors
@@ -221,7 +240,7 @@ int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_
  * Exactly one of value_f32 / value_f64 / value_i8 is the evaluator's value for the side to move.  Terminal
  * leaves use +1 (the reference's inverted sign, mcts.py:125) or -1 when fix_terminal_sign != 0. */
 int qz_mcts_expand_backup(const qz_tree *tree, const uint64_t *mask3, const float *priors, const float *value_f32,
-                          const double *value_f64, const int8_t *value_i8, int fix_terminal_sign,
+                          const double *value_f64, const int8_t *value_i8, double c_puct, int fix_terminal_sign,
                           int32_t *overflow_count, void *stream);
 
 /* Deferred half of qz_mcts_expand_backup: a leaf whose value_i8 was QZ_ROLLOUT_PENDING (its rollout is being
@@ -243,7 +262,14 @@ int qz_mcts_choose(const qz_tree *tree, int mode, double temp, double noise_eps,
 /* MCTS.update_with_move (mcts.py:146-151): dst := the subtree of src under moves[g] (statistics kept,
  * compacted breadth-first) or a fresh root if the move is unknown / negative.  apply_move != 0 also advances
  * root_state by the move (Quoridor.step).  src and dst must be distinct arenas of equal shape. */
-int qz_mcts_reroot(const qz_tree *src, const qz_tree *dst, const int32_t *moves, int apply_move, void *stream);
+int qz_mcts_reroot(const qz_tree *src, const qz_tree *dst, const int32_t *moves, int apply_move, int32_t *overflow_count,
+                   void *stream);
+
+/* `node._children` of ONE node (mcts.py:19-25) for inspection: every legal action in actions() order, children that
+ * never got a slot included.  out_i (int32 [4 + 4*140]): [0] children, [1] the node's visits, [2] its slot; per rank r:
+ * [4+4r] action, [5+4r] slot or -1, [6+4r] visits, [7+4r] in-flight marks.  out_d (f64 [2 + 2*140]): [0] the node's Q,
+ * [1] its prior; per rank r: [2+2r] Q, [3+2r] prior.  One tiny launch; the host-side TreeNode view uses it. */
+int qz_mcts_node_children(const qz_tree *tree, int64_t game, int32_t node, int32_t *out_i, double *out_d, void *stream);
 
 /* Deterministic policy-value stubs for parity testing (tests/golden/stubs.py: kind 1 = S1 uniform, 2 = S2 hash,
  * 3 = S3 hash/8) evaluated on the device: priors f32 [n,140] (0 at illegal actions), values f64 [n]. */

