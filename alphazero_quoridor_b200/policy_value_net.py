@@ -109,6 +109,10 @@ class PolicyValueNet(object):
         self._infer = None
         self._in_buf = None
         self._env = None
+        # the 12-launch inference forward (x chunks) replayed as ONE CUDA graph per batch size: at 8192-position chunks a
+        # layer runs for ~80 us, so launch gaps are a visible share of the AlphaZero path
+        self.use_cuda_graph = bool(use_gpu)
+        self._graphs = {}
 
     # ---- batched device path (the hot one) ----
     @staticmethod
@@ -141,6 +145,7 @@ class PolicyValueNet(object):
         W["head"] = (torch.cat([wv, wp], 0).contiguous(memory_format=torch.channels_last), torch.cat([bv, bp], 0))
         W["fc"] = [(l.weight.detach().to(dt).contiguous(), l.bias.detach().to(dt).contiguous()) for l in (m.fc1, m.fc2, m.fc3)]
         self._infer = W
+        self._graphs = {}                       # captured graphs hold the old weight tensors
         return W
 
     def _infer_forward(self, x):
@@ -159,28 +164,65 @@ class PolicyValueNet(object):
         p = F.log_softmax(F.linear(p, w3, b3).float(), dim=1)
         return p, v
 
+    def _forward_chunks(self, x):
+        m = x.shape[0]
+        if m <= self.max_batch:
+            logp, v = self._infer_forward(x)
+        else:
+            # chunks whose activations (64 ch x 81 x 2 B = 10 KB per position) stay inside the 126 MB L2
+            outs = [self._infer_forward(x[i:i + self.max_batch]) for i in range(0, m, self.max_batch)]
+            logp, v = torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
+        return logp.exp().contiguous(), v.reshape(-1).contiguous()
+
+    def _graph_for(self, m):
+        """Capture the inference forward on the first m rows of the (static) input buffer; returns (graph, probs, value)
+        or None when capture is unavailable (the eager path is used then -- still on the GPU)."""
+        ent = self._graphs.get(m)
+        if ent is not None or not self.use_cuda_graph:
+            return ent
+        x = self._in_buf[:m]
+        try:
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side), torch.no_grad():
+                for _ in range(2):
+                    self._forward_chunks(x)
+            cur.wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.no_grad(), torch.cuda.graph(graph):
+                probs, value = self._forward_chunks(x)
+            ent = (graph, probs, value)
+        except Exception as ex:                 # keep running eagerly, say so once
+            import warnings
+            warnings.warn("CUDA graph capture of the inference forward failed (%r); running it eagerly" % (ex,))
+            self.use_cuda_graph = False
+            ent = None
+        self._graphs[m] = ent
+        return ent
+
     def evaluate_states(self, states):
         """qz_state rows int64 [m,3] (CUDA) -> (probs float32 [m,140], value float32 [m]), all on the device.
-        The encode kernel writes the leaves straight into the net's channels_last bf16 input."""
+        The encode kernel writes the leaves straight into the net's channels_last bf16 input.  The returned tensors
+        are reused by the next call with the same m (consume them in stream order, as the search does)."""
         if self._infer is None:
             self.sync_inference_weights()
         m = states.shape[0]
         if self._in_buf is None or self._in_buf.shape[0] < m:
             self._in_buf = torch.empty((max(m, 1), IN_PAD, 9, 9), dtype=self.infer_dtype, device=self.device,
                                        memory_format=torch.channels_last)
+            self._graphs = {}                   # graphs captured on the old buffer are void
         x = self._in_buf[:m]
         lib = _lib.load()
         with torch.cuda.device(self.device):
             _lib.check(lib.qz_env_encode(_lib.ptr(states), _lib.c_void_p_of(x), _lib.DTYPE_CODE[self.infer_dtype],
                                          _lib.LAYOUT_NHWC, IN_PAD, m, _lib.stream_ptr(self.device)), "qz_env_encode")
-        with torch.no_grad():
-            if m <= self.max_batch:
-                logp, v = self._infer_forward(x)
-            else:
-                # chunks whose activations (64 ch x 81 x 2 B = 10 KB per position) stay inside the 126 MB L2
-                outs = [self._infer_forward(x[i:i + self.max_batch]) for i in range(0, m, self.max_batch)]
-                logp, v = torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0)
-        return logp.exp().contiguous(), v.reshape(-1).contiguous()
+            ent = self._graph_for(m) if m > 0 else None
+            if ent is not None:
+                ent[0].replay()
+                return ent[1], ent[2]
+            with torch.no_grad():
+                return self._forward_chunks(x)
 
     # ---- reference API ----
     def _f32(self, x):

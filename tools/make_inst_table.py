@@ -5,7 +5,7 @@ build, from an ncu capture of the very command bench.py runs (seeded => the same
     python tools/make_inst_table.py [--plies 26]          # on the GPU box (gpurun); ~10-15 min under ncu
 
 Runs `ncu --profile-from-start off --metrics smsp__inst_executed.sum,smsp__thread_inst_executed.sum,
-gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum python bench.py --steps <plies> --warmup 0 --ncu-range
+gpu__time_duration.sum python bench.py --steps <plies> --warmup 0 --ncu-range
 ...`, splits the launch list into plies at every qz_mcts_choose_kernel launch (one per ply) and sums per kernel.
 bench.py divides these counts by its own CUDA-event time for the same plies: `roofline.frac`.
 """
@@ -23,8 +23,9 @@ sys.path.insert(0, ROOT)
 
 import bench  # noqa: E402
 
-METRICS = ["smsp__inst_executed.sum", "smsp__thread_inst_executed.sum", "gpu__time_duration.sum", "dram__bytes_read.sum",
-           "dram__bytes_write.sum"]
+# one ncu pass: more metrics (e.g. dram__bytes_*) force kernel replay, and replay saves / restores every writable
+# allocation around each of the ~15,000 launches (the first attempt ran 27 minutes and died)
+METRICS = ["smsp__inst_executed.sum", "smsp__thread_inst_executed.sum", "gpu__time_duration.sum"]
 
 
 def short(name):
