@@ -22,9 +22,10 @@
 //   child slot : prior, visits, q, child_base (-1 = is_leaf(), >= 0 = its block, <= -2 = moved to slot -2 - x),
 //                meta = action | actions() rank << 8 | in-flight (virtual loss) count << 16
 //   header b   : q[b..b+2] = legal mask bits; visits[b] = m, visits[b+1] = cap, visits[b+2] = legal count;
-//                net priors only: child_base[b] = row of the prior pool, child_base[b+1] = candidate action (-1 = none),
-//                prior[b] = its prior, {meta[b], meta[b+1], meta[b+2], child_base[b+2], bits of prior[b+1]} = the 140-bit
-//                set of actions that already have a slot
+//                net priors only: child_base[b] = offset of the node's priors in the game's prior pool (one float per
+//                legal action, in actions() rank order), child_base[b+1] = rank of the candidate (-1 = none), prior[b] =
+//                its prior, {meta[b], meta[b+1], meta[b+2], child_base[b+2], bits of prior[b+1]} = the set of ranks that
+//                already have a slot
 // 24 B per visited child + ~7 slots per expansion: ~0.3 MB per game for 1000 playouts (3.4 MB with eager children).
 //
 // Exactness: Q and u are evaluated in float64 with numpy's promotion rules (float32 prior * weak Python
@@ -62,7 +63,7 @@ __device__ __forceinline__ QzGameTree qz_game_tree(const qz_tree &t, int64_t g) 
     const int64_t o = g * t.node_cap;
     QzGameTree v;
     v.prior = t.prior + o; v.visits = t.visits + o; v.q = t.q + o; v.child_base = t.child_base + o; v.meta = t.node_meta + o;
-    v.pool = t.prior_pool ? t.prior_pool + g * (int64_t)t.pool_cap * QZ_N_ACTIONS : nullptr;
+    v.pool = t.prior_pool ? t.prior_pool + g * (int64_t)t.pool_cap : nullptr;
     return v;
 }
 // follow the forwarding indices a relocated block left behind
@@ -99,29 +100,29 @@ __device__ __forceinline__ int qz_action_of_rank(uint32_t pawn, uint64_t hl, uin
     return found;
 }
 // net priors: the unvisited child the reference's first-max would reach first = largest float32 product c_puct * P
-// (mcts.py:69 promotes that product to float64), lowest rank on ties, among the legal actions without a slot
-__device__ __forceinline__ void qz_next_candidate(const float *__restrict__ row, uint32_t pawn, uint64_t hl, uint64_t vl,
-                                                  const uint32_t mat[5], float c_puct_f, int &nact, float &nprior) {
+// (mcts.py:69 promotes that product to float64), lowest rank on ties, among the children without a slot.  `row` holds the
+// node's priors in actions() RANK order (`total` of them), `mat` the ranks that already have a slot.
+__device__ __forceinline__ void qz_next_candidate(const float *__restrict__ row, int total, const uint32_t mat[5],
+                                                  float c_puct_f, int &nrank, float &nprior) {
     const int lane = threadIdx.x & 31;
     float bcp = -INFINITY, bp = 0.0f;
-    int brank = 0x7FFFFFFF, ba = -1;
+    int brank = -1;
 #pragma unroll
     for (int r = 0; r < 5; r++) {
-        const int a = lane + 32 * r;
-        if (a >= QZ_N_ACTIONS || !qz_is_legal(pawn, hl, vl, a) || ((mat[r] >> lane) & 1u)) continue;
-        const float p = row[a], cp = c_puct_f * p;
-        const int rank = qz_action_rank(pawn, hl, vl, a);
-        if (cp > bcp || (cp == bcp && rank < brank) || ba < 0) { bcp = cp; brank = rank; bp = p; ba = a; }
+        const int rank = lane + 32 * r;
+        if (rank >= total || ((mat[r] >> lane) & 1u)) continue;
+        const float p = row[rank], cp = c_puct_f * p;
+        if (brank < 0 || cp > bcp) { bcp = cp; brank = rank; bp = p; }   // ascending rank per lane: first max kept
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         const float ocp = __shfl_xor_sync(QZ_FULL_MASK, bcp, off), op = __shfl_xor_sync(QZ_FULL_MASK, bp, off);
-        const int orank = __shfl_xor_sync(QZ_FULL_MASK, brank, off), oa = __shfl_xor_sync(QZ_FULL_MASK, ba, off);
-        if (oa >= 0 && (ba < 0 || ocp > bcp || (ocp == bcp && orank < brank))) { bcp = ocp; brank = orank; bp = op; ba = oa; }
+        const int orank = __shfl_xor_sync(QZ_FULL_MASK, brank, off);
+        if (orank >= 0 && (brank < 0 || ocp > bcp || (ocp == bcp && orank < brank))) { bcp = ocp; brank = orank; bp = op; }
     }
-    nact = ba; nprior = bp;
+    nrank = brank; nprior = bp;
 }
-// header words holding the "has a slot" set: bit (a & 31) of word a >> 5
+// header words holding the "has a slot" set by rank: bit (r & 31) of word r >> 5
 __device__ __forceinline__ void qz_mat_load(const QzGameTree &v, int b, uint32_t mat[5]) {
     mat[0] = v.meta[b]; mat[1] = v.meta[b + 1]; mat[2] = v.meta[b + 2]; mat[3] = (uint32_t)v.child_base[b + 2];
     mat[4] = __float_as_uint(v.prior[b + 1]);
@@ -265,15 +266,15 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
                 if (UNIFORM_PRIOR) {
                     cpu = uni; urank = m;                                // slots are made in actions() order
                 } else {
-                    uprior = prior[b]; uact = child_base[b + 1];
+                    uprior = prior[b]; urank = child_base[b + 1];
                     cpu = (double)(c_puct_f * uprior);
-                    urank = qz_action_rank(pawn, hl, vl, uact);
                 }
                 const double u0 = cpu * sq / (double)(1 + 0 + 0);
                 take_new = bj < 0 || u0 > best || (u0 == best && urank < brank);
             }
             if (take_new) {
-                if (UNIFORM_PRIOR) { uact = qz_action_of_rank(pawn, hl, vl, urank); uprior = 1.0f / (float)total; }
+                uact = qz_action_of_rank(pawn, hl, vl, urank);
+                if (UNIFORM_PRIOR) uprior = 1.0f / (float)total;
                 int cap = visits[b + 1];
                 bool room = true;
                 if (m == cap) {
@@ -312,11 +313,11 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
                         uint32_t mat[5];
                         qz_mat_load(v, b, mat);
 #pragma unroll
-                        for (int r = 0; r < 5; r++) if (r == (uact >> 5)) mat[r] |= 1u << (uact & 31);
-                        int nact; float nprior;
-                        qz_next_candidate(v.pool + (int64_t)child_base[b] * QZ_N_ACTIONS, pawn, hl, vl, mat, c_puct_f, nact, nprior);
+                        for (int r = 0; r < 5; r++) if (r == (urank >> 5)) mat[r] |= 1u << (urank & 31);
+                        int nrank; float nprior;
+                        qz_next_candidate(v.pool + child_base[b], total, mat, c_puct_f, nrank, nprior);
                         __syncwarp();
-                        if (lane == 0) { qz_mat_store(v, b, mat); child_base[b + 1] = nact; prior[b] = nprior; }
+                        if (lane == 0) { qz_mat_store(v, b, mat); child_base[b + 1] = nrank; prior[b] = nprior; }
                     }
                     if (at_root) {
                         if (lane == 0) {
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(128) qz_mcts_expand_backup_kernel(qz_tree t, Q
                 if (cnt > 0) {
                     // every child of the root is visited sooner or later; elsewhere a handful are
                     const int cap = node == root ? cnt : min(cnt, QZ_CAP0);
-                    if (n_nodes + QZ_HDR + cap <= t.node_cap && (!a.priors || n_pool < t.pool_cap)) {
+                    if (n_nodes + QZ_HDR + cap <= t.node_cap && (!a.priors || n_pool + cnt <= t.pool_cap)) {
                         const int b = n_nodes;
                         n_nodes += QZ_HDR + cap;
                         if (lane < QZ_HDR) {
@@ -436,19 +437,21 @@ __global__ void __launch_bounds__(128) qz_mcts_expand_backup_kernel(qz_tree t, Q
                             child_base[b + lane] = lane == 2 ? 0 : -1;
                         }
                         if (a.priors) {
-                            float *row = tv.pool + (int64_t)n_pool * QZ_N_ACTIONS;
+                            // the node's priors in actions() rank order: `cnt` floats of the game's prior pool
+                            float *row = tv.pool + n_pool;
 #pragma unroll
                             for (int r = 0; r < 5; r++) {
                                 const int act = lane + 32 * r;
-                                if (act < QZ_N_ACTIONS) row[act] = qz_is_legal(pawn, hl, vl, act) ? a.priors[L * QZ_N_ACTIONS + act] : 0.0f;
+                                if (act < QZ_N_ACTIONS && qz_is_legal(pawn, hl, vl, act))
+                                    row[qz_action_rank(pawn, hl, vl, act)] = a.priors[L * QZ_N_ACTIONS + act];
                             }
                             __syncwarp();
                             const uint32_t mat[5] = {0, 0, 0, 0, 0};
-                            int nact; float nprior;
-                            qz_next_candidate(row, pawn, hl, vl, mat, a.c_puct_f, nact, nprior);
+                            int nrank; float nprior;
+                            qz_next_candidate(row, cnt, mat, a.c_puct_f, nrank, nprior);
                             __syncwarp();
-                            if (lane == 0) { child_base[b] = n_pool; child_base[b + 1] = nact; prior[b] = nprior; }
-                            n_pool++;
+                            if (lane == 0) { child_base[b] = n_pool; child_base[b + 1] = nrank; prior[b] = nprior; }
+                            n_pool += cnt;
                         }
                         __syncwarp();
                         if (lane == 0) child_base[node] = b;
@@ -628,7 +631,7 @@ __global__ void qz_mcts_node_children_kernel(qz_tree t, int64_t g, int32_t node,
         const int r = qz_action_rank(pawn, hl, vl, act);
         out_i[4 + 4 * r] = act; out_i[5 + 4 * r] = -1; out_i[6 + 4 * r] = 0; out_i[7 + 4 * r] = 0;
         out_d[2 + 2 * r] = 0.0;
-        out_d[3 + 2 * r] = (double)((pidx >= 0 && v.pool) ? v.pool[(int64_t)pidx * QZ_N_ACTIONS + act] : 1.0f / (float)total);
+        out_d[3 + 2 * r] = (double)((pidx >= 0 && v.pool) ? v.pool[pidx + r] : 1.0f / (float)total);
     }
     __syncwarp();
     for (int j = lane; j < m; j += 32) {
@@ -847,7 +850,7 @@ __global__ void __launch_bounds__(128) qz_mcts_reroot_kernel(qz_tree src, qz_tre
                 const int m = sv.visits[sb], total = sv.visits[sb + 2];
                 const int cap = slot == 0 ? total : min(total, max(m + (m >> 1) + 1, QZ_CAP0));
                 const int spool = sv.child_base[sb];
-                if (full || tail + QZ_HDR + cap > dst.node_cap || (spool >= 0 && n_pool >= dst.pool_cap)) {
+                if (full || tail + QZ_HDR + cap > dst.node_cap || (spool >= 0 && n_pool + total > dst.pool_cap)) {
                     // cannot happen with arenas of equal shape (the kept subtree is a subset); be safe: cut the subtree here
                     full = true;
                     __syncwarp();
@@ -863,10 +866,10 @@ __global__ void __launch_bounds__(128) qz_mcts_reroot_kernel(qz_tree src, qz_tre
                     dv.child_base[db + lane] = lane == 0 ? (spool >= 0 ? n_pool : -1) : sv.child_base[sb + lane];
                 }
                 if (spool >= 0) {
-                    const float *srow = sv.pool + (int64_t)spool * QZ_N_ACTIONS;
-                    float *drow = dv.pool + (int64_t)n_pool * QZ_N_ACTIONS;
-                    for (int a = lane; a < QZ_N_ACTIONS; a += 32) drow[a] = srow[a];
-                    n_pool++;
+                    const float *srow = sv.pool + spool;
+                    float *drow = dv.pool + n_pool;
+                    for (int a = lane; a < total; a += 32) drow[a] = srow[a];
+                    n_pool += total;
                 }
                 for (int j = lane; j < m; j += 32) {
                     const int sc = sb + QZ_HDR + j, dc = db + QZ_HDR + j;

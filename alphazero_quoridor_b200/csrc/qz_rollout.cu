@@ -10,8 +10,6 @@
 // first capture (profiles/r1a_rollout_ncu_full.txt) of the single-kernel form showed 4.2 active lanes per
 // instruction because a warp mixed both kinds.  No tensor cores: the game lives in registers (the pawn phase
 // adds a byte-per-tile table in shared memory) and HBM sees 24 B in, 48 B through `mid`, 1..29 B out per ROLLOUT.
-#include <stdlib.h>
-
 #include "qz_common.cuh"
 #include "qz_sample.cuh"
 #include "qz_warp.cuh"
@@ -40,7 +38,6 @@ struct QzRolloutArgs {
     unsigned long long *count_out;
     unsigned long long *work;      // work counter of this pass
     int32_t slice;                 // plies a rollout may play per pass
-    int64_t ring_cap;              // queue form: entries of the survivor ring (list_out)
 };
 
 // Warp-aggregated claim of the next unstarted rollout for every idle lane; returns -1 when none is left.
@@ -470,209 +467,6 @@ __global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_kernel(QzR
     if ((tid & 31) == 0 && my_plies) atomicAdd(a.counter + 1, my_plies);
 }
 
-// ---- phase 2, one launch: the same plies with an in-kernel survivor queue ---------------------------------------
-// The sliced passes above re-pack the survivors of a slice into full warps, but every pass is a launch of its own
-// that ends when its last warp does, and the later passes run a handful of long rollouts on a mostly idle chip
-// (profiles/r1p_bench_launches.txt: 16 pawn launches per wave at 44 % issue activity, the first one alone reaches 76 %).
-// Here ONE resident grid plays the whole pawn phase.  A rollout whose slice is used up is parked (only its meta word
-// changes) and its id appended to a ring in the workspace; idle lanes claim work -- first the rollouts not started yet,
-// then ring entries -- eight or more at a time, so the expensive set-up still runs in groups.  Nothing ever waits for
-// a thread that is not already running: a claimed ring entry was reserved by a running lane that is about to write it,
-// and a warp with nothing to do polls the finished-rollout count, so the kernel cannot deadlock whatever else shares
-// the GPU.  The plies, draws and results of a rollout are exactly those of the sliced form.
-__device__ __forceinline__ QzState qz_load_state_cg(const qz_state *p) {      // coherent (L2) load: `mid` is rewritten
-    const uint64_t *q = reinterpret_cast<const uint64_t *>(p);                  // by other SMs while this kernel runs
-    QzState s;
-    s.H = __ldcg(q); s.V = __ldcg(q + 1); s.meta = __ldcg(q + 2);
-    return s;
-}
-
-__global__ void __launch_bounds__(QZ_PAWN_THREADS, 8) qz_rollout_pawn_queue_kernel(QzRolloutArgs a) {
-    __shared__ QzPawnSmem sm;
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (tid < 12) sm.delta[tid] = qz_delta(tid);
-    __syncthreads();
-    const uint8_t *my_tile = reinterpret_cast<const uint8_t *>(sm.tile + tid * QZ_TILE_TABLE_WORDS);
-    const int64_t total = a.count_in ? (int64_t)*a.count_in : a.n_rollouts;
-    unsigned long long *head = a.work, *tail = a.work + 1, *done = a.work + 2;
-    int32_t *ring = a.list_out;
-    const int64_t ring_cap = a.ring_cap;
-    QzPhilox4 cur = {0, 0, 0, 0}, nxt = {0, 0, 0, 0};
-    uint64_t rid = 0;
-    int64_t r = -1;
-    int L = 0, O = 0, mover = 1, steps = 0, steps0 = 0, player0 = 0, left = 0;
-    uint32_t iL = 0, iO = 0;
-    unsigned long long my_plies = 0;
-    for (unsigned iter = 0;; iter++) {
-        const bool want = r < 0;
-        const unsigned want_lanes = __ballot_sync(QZ_FULL_MASK, want);
-        const unsigned busy_lanes = ~want_lanes;
-        if ((iter & 3u) == 0 && r >= 0) nxt = qz_philox(a.seed, rid, ((uint32_t)steps >> 2) + 1u, 0);
-        int settled = 0;                                                 // rollouts this lane finished in this iteration
-        if (want_lanes && (busy_lanes == 0 || __popc(want_lanes) >= QZ_PAWN_REFILL)) {
-            bool need = want, fresh = false;
-            uint64_t H = 0, V = 0;
-            for (;;) {
-                const unsigned nm = __ballot_sync(QZ_FULL_MASK, need);
-                if (!nm) break;
-                // the leader claims as many EXISTING items (unstarted rollouts, then ring entries) as lanes need
-                const int leader = __ffs(nm) - 1;
-                long long base = 0;
-                int got_n = 0;
-                if (lane == leader) {
-                    for (;;) {
-                        const unsigned long long h = *(volatile unsigned long long *)head, t = *(volatile unsigned long long *)tail;
-                        const long long avail = (long long)total + (long long)t - (long long)h;
-                        if (avail <= 0) break;
-                        const int c = avail < (long long)__popc(nm) ? (int)avail : __popc(nm);
-                        if (atomicCAS(head, h, h + (unsigned long long)c) == h) { base = (long long)h; got_n = c; break; }
-                    }
-                }
-                base = __shfl_sync(QZ_FULL_MASK, base, leader);
-                got_n = __shfl_sync(QZ_FULL_MASK, got_n, leader);
-                if (got_n == 0) break;                                   // nothing to claim right now
-                const int my_rank = __popc(nm & ((1u << lane) - 1u));
-                if (need && my_rank < got_n) {
-                    const long long idx = base + my_rank;
-                    int64_t got;
-                    if (idx < total) {
-                        got = a.list_in ? (int64_t)a.list_in[idx] : (int64_t)idx;
-                    } else {
-                        volatile int32_t *slot = ring + (idx - total) % ring_cap;
-                        int32_t v;
-                        while ((v = *slot) == 0) { }                     // reserved by a running lane: written at once
-                        *slot = 0;
-                        __threadfence();                                 // the parked meta word was stored before the id
-                        got = (int64_t)v - 1;
-                    }
-                    const QzState s = qz_load_state_cg(a.mid + got);
-                    const uint64_t m0 = __ldg(reinterpret_cast<const uint64_t *>(a.states + qz_start_index(a, got)) + 2);
-                    const unsigned fl = qz_flags(s.meta);
-                    const int st = (int)qz_ply(s.meta) - (int)qz_ply(m0);
-                    if (fl & QZ_FLAG_PENDING) {                          // deferred: finished later by qz_rollout_finish
-                        a.result[got] = (int8_t)-128;
-                        settled++;
-                    } else if ((fl & (QZ_FLAG_DONE | QZ_FLAG_STALEMATE)) || st >= a.limit - 1 ||
-                               (qz_w1(s.meta) + qz_w2(s.meta)) != 0 || !qz_on_board(s.meta)) {
-                        a.result[got] = qz_pawn_result(qz_winner(s.meta), qz_cur(m0));      // ended in the wall phase
-                        if (a.plies) a.plies[got] = st;
-                        if (a.final_states) qz_store_state(a.final_states + got, s);
-                        my_plies += (unsigned long long)st;
-                        settled++;
-                    } else {
-                        r = got; need = false; fresh = true;
-                        H = s.H; V = s.V;
-                        mover = qz_cur(s.meta);
-                        L = mover == 1 ? qz_p1(s.meta) : qz_p2(s.meta);
-                        O = mover == 1 ? qz_p2(s.meta) : qz_p1(s.meta);
-                        steps = steps0 = st;
-                        left = a.slice;
-                        player0 = qz_cur(m0);
-                        rid = a.rids ? __ldg(a.rids + got) : a.rid_base + (uint64_t)got;
-                    }
-                }
-            }
-            if (fresh) {
-                cur = qz_philox(a.seed, rid, (uint32_t)steps >> 2, 0);
-                nxt = qz_philox(a.seed, rid, ((uint32_t)steps >> 2) + 1u, 0);
-                const QzPawnCtx c = qz_ctx_build(H, V);
-                qz_tile_table(c, sm.tile + tid * QZ_TILE_TABLE_WORDS, 1);
-                uint32_t *hm = sm.hmask + tid;
-                hm[0 * QZ_PAWN_THREADS] = c.neH.w0; hm[1 * QZ_PAWN_THREADS] = c.neH.w1; hm[2 * QZ_PAWN_THREADS] = c.neH.w2;
-                hm[3 * QZ_PAWN_THREADS] = c.nwH.w0; hm[4 * QZ_PAWN_THREADS] = c.nwH.w1; hm[5 * QZ_PAWN_THREADS] = c.nwH.w2;
-                hm[6 * QZ_PAWN_THREADS] = c.seH.w0; hm[7 * QZ_PAWN_THREADS] = c.seH.w1; hm[8 * QZ_PAWN_THREADS] = c.seH.w2;
-                hm[9 * QZ_PAWN_THREADS] = c.swH.w0; hm[10 * QZ_PAWN_THREADS] = c.swH.w1; hm[11 * QZ_PAWN_THREADS] = c.swH.w2;
-                iL = my_tile[L];
-                iO = my_tile[O];
-            }
-        }
-        if (r >= 0) {
-            // one ply (quoridor.py:146,159-186 with no wall left; pure_mcts.py:7-10,97-103) -- as in the sliced kernel
-            uint32_t hO = 0;
-            if (qz_pawn_contact(iL, L, O) & 0xCu) {
-                const uint32_t *hm = sm.hmask + (O >> 5) * QZ_PAWN_THREADS + tid;
-                const int sh = O & 31;
-                hO = ((hm[0] >> sh) & 1u) | (((hm[3 * QZ_PAWN_THREADS] >> sh) & 1u) << 1) |
-                     (((hm[6 * QZ_PAWN_THREADS] >> sh) & 1u) << 2) | (((hm[9 * QZ_PAWN_THREADS] >> sh) & 1u) << 3);
-            }
-            uint32_t pm = qz_pawn_moves_info(iL, iO, hO, L, O, mover);
-            const int np = __popc(pm);
-            int winner = 0;
-            unsigned add_flags = 0;
-            bool finished = false;
-            if (np == 0) {
-                add_flags = QZ_FLAG_STALEMATE;
-                finished = true;
-            } else {
-                const uint32_t word = qz_philox_word(cur, steps & 3);
-                int k = (int)__umulhi(word, (uint32_t)np);
-                if (k > 0) pm &= pm - 1;
-                if (k > 1) pm &= pm - 1;
-                if (k > 2) pm &= pm - 1;
-                for (k -= 3; k > 0; k--) pm &= pm - 1;
-                L += sm.delta[__ffs(pm) - 1];
-                steps++;
-                if ((steps & 3) == 0) cur = nxt;
-                if (mover == 1 ? L > 71 : L < 9) {
-                    winner = mover;
-                    add_flags = QZ_FLAG_DONE | ((unsigned)winner << QZ_FLAG_WINNER_SHIFT);
-                    finished = true;
-                } else {
-                    const int t = L; L = O; O = t;
-                    const uint32_t moved = my_tile[O];
-                    iL = iO; iO = moved;
-                    mover = 3 - mover;
-                    finished = steps >= a.limit - 1;
-                    if (!finished && --left == 0) {
-                        // slice used up: park the rollout and hand it to whichever lanes refill next
-                        uint64_t *mw = reinterpret_cast<uint64_t *>(a.mid + r) + 2;
-                        const uint64_t m = __ldcg(mw);
-                        const unsigned ply = qz_ply(m) + (unsigned)(steps - steps0);
-                        *mw = qz_pack_meta(mover == 1 ? L : O, mover == 1 ? O : L, 0, 0, mover, qz_flags(m),
-                                           ply < 0xFFFFu ? ply : 0xFFFFu);
-                        __threadfence();
-                        const unsigned long long p = atomicAdd(tail, 1ull);
-                        volatile int32_t *slot = ring + (int64_t)(p % (unsigned long long)ring_cap);
-                        while (*slot != 0) { }                           // never spins: at most n_rollouts entries are live
-                        *slot = (int32_t)r + 1;
-                        r = -1;
-                    }
-                }
-            }
-            if (finished && r >= 0) {
-                a.result[r] = qz_pawn_result(winner, player0);
-                if (a.plies) a.plies[r] = steps;
-                if (a.final_states) {
-                    QzState s = qz_load_state_cg(a.mid + r);
-                    const unsigned ply = qz_ply(s.meta) + (unsigned)(steps - steps0);
-                    s.meta = qz_pack_meta(mover == 1 ? L : O, mover == 1 ? O : L, 0, 0, mover, qz_flags(s.meta) | add_flags,
-                                          ply < 0xFFFFu ? ply : 0xFFFFu);
-                    qz_store_state(a.final_states + r, s);
-                }
-                my_plies += (unsigned long long)steps;
-                settled++;
-                r = -1;
-            }
-        }
-        // account for the rollouts settled in this iteration; a warp with nothing in hand leaves once all are
-        int n_settled = settled;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) n_settled += __shfl_xor_sync(QZ_FULL_MASK, n_settled, off);
-        if (n_settled && lane == 0) atomicAdd(done, (unsigned long long)n_settled);
-        if (__all_sync(QZ_FULL_MASK, r < 0)) {
-            unsigned long long d = 0;
-            if (lane == 0) d = *(volatile unsigned long long *)done;
-            d = __shfl_sync(QZ_FULL_MASK, d, 0);
-            if ((long long)d >= (long long)total) break;
-            const unsigned long long h = *(volatile unsigned long long *)head, t = *(volatile unsigned long long *)tail;
-            if ((long long)total + (long long)t - (long long)h <= 0) __nanosleep(256);       // queue dry: others still play
-        }
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) my_plies += __shfl_xor_sync(QZ_FULL_MASK, my_plies, off);
-    if (lane == 0 && my_plies) atomicAdd(a.counter + 1, my_plies);
-}
-
 // workspace: header | mid[n] | stuck_list[n] | two survivor lists [n] (ping-pong between pawn passes)
 #define QZ_WS_COUNTERS 64
 #define QZ_WS_HEADER_BYTES (QZ_WS_COUNTERS * 8)
@@ -709,39 +503,13 @@ static int64_t qz_pawn_slice(int64_t limit, int *passes) {
     return slice;
 }
 
-static bool qz_pawn_sliced() {
-    static const bool sliced = getenv("QZ_PAWN_SLICED") != nullptr;     // A/B knob for measurements (default: queue form)
-    return sliced;
-}
-
 extern "C" int32_t qz_rollout_pawn_passes(int32_t limit) {
     int passes = 0;
     qz_pawn_slice(limit, &passes);
-    return qz_pawn_sliced() ? passes : 1;
-}
-
-// Queue form: one launch.  Counters: [8] claimed, [9] appended to the ring, [10] settled.
-static int qz_pawn_queue(QzRolloutArgs a, bool finish, cudaStream_t st, const char *what) {
-    int passes = 0;
-    a.slice = (int32_t)qz_pawn_slice(a.limit, &passes);
-    a.work = a.counter + 8;
-    a.list_in = finish ? a.stuck_list : nullptr;
-    a.count_in = finish ? a.counter + 3 : nullptr;
-    a.list_out = a.stuck_list + qz_list_bytes(a.n_rollouts) / 4;         // the two survivor lists as one ring
-    a.ring_cap = 2 * (qz_list_bytes(a.n_rollouts) / 4);
-    a.count_out = nullptr;
-    // an empty ring is all zeros (an entry is id + 1); the kernel leaves it empty, this guards against a caller's
-    // uninitialised or reused workspace
-    cudaError_t e = cudaMemsetAsync(a.list_out, 0, (size_t)a.ring_cap * 4, st);
-    if (e != cudaSuccess) return qz_fail((int)e, "%s: memset: %s", what, cudaGetErrorString(e));
-    int blocks = qz_persistent_blocks((const void *)qz_rollout_pawn_queue_kernel, a.n_rollouts, QZ_PAWN_THREADS);
-    if (finish) blocks = blocks / 4 > 0 ? blocks / 4 : 1;
-    qz_rollout_pawn_queue_kernel<<<blocks, QZ_PAWN_THREADS, 0, st>>>(a);
-    return qz_check_launch(what);
+    return passes;
 }
 
 static int qz_pawn_passes(QzRolloutArgs a, bool finish, cudaStream_t st, const char *what) {
-    if (!qz_pawn_sliced()) return qz_pawn_queue(a, finish, st, what);
     int passes = 0;
     const int64_t slice = qz_pawn_slice(a.limit, &passes);
     int32_t *lists[2] = {a.stuck_list + qz_list_bytes(a.n_rollouts) / 4, a.stuck_list + 2 * (qz_list_bytes(a.n_rollouts) / 4)};
@@ -784,7 +552,6 @@ static int qz_rollout_args(QzRolloutArgs &a, const qz_state *states, int64_t n_s
     a.mid = (qz_state *)((char *)workspace + QZ_WS_HEADER_BYTES);
     a.stuck_list = (int32_t *)((char *)workspace + QZ_WS_HEADER_BYTES + n_rollouts * (int64_t)sizeof(qz_state));
     a.list_in = nullptr; a.count_in = nullptr; a.list_out = nullptr; a.count_out = nullptr; a.work = nullptr; a.slice = 0;
-    a.ring_cap = 0;
     return 0;
 }
 

@@ -214,15 +214,16 @@ class TrainPipeline(object):
         """train.py:55-63: play until >= n_games more games have finished; extend the replay buffer.  The samples
         go from the self-play record tensors to the replay ring on the device (one append per flush)."""
         sp = self._engine()
-        finished = steps = 0
-        while finished < n_games and steps < max_steps:
+        steps = 0
+        start = int(sp.finished_games.item())
+        while int(sp.finished_games.item()) - start < n_games and steps < max_steps:
             sp.step()
             steps += 1
             for st, pr, z, lens in sp.flushed:
                 self.data_buffer.extend(st, pr, z)
-                finished += int(lens.numel())
                 self.episode_len = int(lens[-1].item()) if lens.numel() else self.episode_len
             sp.flushed = []
+        finished = int(sp.finished_games.item()) - start
         sp.check_overflow()
         return finished
 

@@ -43,8 +43,9 @@ class _Arena:
 
     def __init__(self, n, cap, dev, pool_cap=0):
         tot = n * cap
-        # stored (non-uniform) priors: one row of 140 per expanded node (children get their slot when first visited)
-        self.prior_pool = torch.empty(n * pool_cap * 140, dtype=torch.float32, device=dev) if pool_cap else None
+        # stored (non-uniform) priors: one float per legal action of every expanded node (children get their slot when
+        # first visited); pool_cap floats per game
+        self.prior_pool = torch.empty(n * pool_cap, dtype=torch.float32, device=dev) if pool_cap else None
         self.n_pool = torch.zeros(n, dtype=torch.int32, device=dev) if pool_cap else None
         self.prior = torch.empty(tot, dtype=torch.float32, device=dev)
         self.visits = torch.empty(tot, dtype=torch.int32, device=dev)
@@ -170,7 +171,7 @@ class NetEvaluator:
 class BatchedMCTS:
     def __init__(self, n_games, evaluator, c_puct=5, n_playout=100, leaves_per_game=1, node_cap=None,
                  max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None, defer_depth=0,
-                 defer_until_drain=False, allow_large_k=False):
+                 defer_until_drain=False, allow_large_k=False, reuse_factor=4):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda")
@@ -191,15 +192,19 @@ class BatchedMCTS:
                              "(pass allow_large_k=True to override)" % (self.K, MAX_K_NONUNIFORM))
         self.fix_terminal_sign = bool(fix_terminal_sign)
         self.max_depth = int(max_depth)
-        # playouts whose nodes one arena may have to hold: one search, or two with tree reuse (the kept subtree of the
-        # previous move plus this move's playouts; a sharply peaked search can keep more -- the overflow counter tells)
-        kept = self.n_playout * (2 if reuse_tree else 1) + self.K
+        # playouts whose nodes one arena may have to hold: one search, or -- with tree reuse -- this move's playouts plus
+        # the subtree kept from the moves before.  The reference keeps that subtree without bound (mcts.py:146-151); in
+        # forced late-game lines a search keeps most of itself (the recorded reference runs reach 3.5 x n_playout kept
+        # visits), so the default holds (reuse_factor + 1) searches; the overflow counter tells when that was too little.
+        kept = self.n_playout * ((reuse_factor + 1) if reuse_tree else 1) + self.K
         if node_cap is None:
             # lazy children: a playout adds at most one child slot (<= 4 amortised with block doubling and the copies
             # it leaves behind) and one block (3 header + 4 child slots); the root's block holds all <= 140 children
             node_cap = 160 + kept * SLOTS_PER_PLAYOUT
         self.node_cap = int(node_cap)
-        self.pool_cap = 0 if self.uniform_prior else kept + 1
+        # prior pool: room for two searches of full-width nodes (140 floats each); the deep kept trees live in late
+        # positions whose nodes have a handful of legal actions, i.e. a handful of floats
+        self.pool_cap = 0 if self.uniform_prior else (self.n_playout * (2 if reuse_tree else 1) + self.K + 1) * MAX_CHILDREN
         dev = self.device
         self.arenas = [_Arena(self.n, self.node_cap, dev, self.pool_cap)]
         if reuse_tree:

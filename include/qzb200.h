@@ -183,7 +183,8 @@ int qz_rollout_finish(const qz_state *states, int64_t n_states, const int32_t *s
  *   child slot : prior f32 (TreeNode._P), visits i32 (_n_visits), q f64 (_Q), child_base i32 (-1 = is_leaf(), >= 0 = its
  *                block, <= -2 = moved to slot -2 - x), node_meta u32 = action | actions() rank << 8 | in-flight << 16
  *   per game   : root (slot index, always 0 after init/reroot), n_nodes (bump allocator), root_state;
- *                with stored (non-uniform) priors: prior_pool rows of 140 f32, one per expanded node, n_pool rows used
+ *                with stored (non-uniform) priors: prior_pool, pool_cap floats per game -- an expanded node keeps one
+ *                float per legal action, in actions() order -- and n_pool, the floats in use
  *   per leaf   : (n_games * leaves_per_game entries, refilled by every select) leaf_node, leaf_state,
  *                path[max_depth] + path_len (root..leaf slot indices), leaf_flags (QZ_LEAF_*)
  * Sizing: a playout adds at most one child slot (amortised <= 4 with block doubling) and one block (3 + 4 slots), the
@@ -195,7 +196,7 @@ typedef struct qz_tree {
     int32_t node_cap;
     int32_t max_depth;
     int32_t leaves_per_game;
-    int32_t pool_cap;           /* rows of prior_pool per game (0 = uniform priors only) */
+    int32_t pool_cap;           /* floats of prior_pool per game (0 = uniform priors only) */
     float *prior;
     int32_t *visits;
     double *q;
@@ -209,7 +210,7 @@ typedef struct qz_tree {
     int32_t *path;
     int32_t *path_len;
     uint8_t *leaf_flags;
-    float *prior_pool;          /* [n_games * pool_cap * 140] or NULL */
+    float *prior_pool;          /* [n_games * pool_cap] or NULL */
     int32_t *n_pool;            /* [n_games] or NULL */
 } qz_tree;
 

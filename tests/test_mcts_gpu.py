@@ -57,6 +57,7 @@ def test_mcts_golden_reference_api(qz, mcts_golden, idx):
         assert qs == mv["q"], case["name"]                       # float64, bit-exact
         assert (rn, rq) == (mv["root_visits"], mv["root_q"])
         np.testing.assert_allclose(probs, np.array(mv["probs"]), rtol=1e-12, atol=1e-300)
+        assert tree._engine.overflow_count() == 0               # an overflowing arena would silently cost exactness
         if i + 1 < len(case["moves"]):
             tree.update_with_move(mv["move"])
             g.step(mv["move"])
@@ -129,6 +130,7 @@ def test_tree_reuse_and_moves_vs_oracle(qz):
         eng.advance(torch.from_numpy(moves))
         # finished games keep being searched on the device (terminal root); only live ones are compared
     assert sum(alive) > n // 2
+    assert eng.overflow_count() == 0
 
 
 def test_fix_terminal_sign_switch(qz):
