@@ -43,7 +43,8 @@ SIGNATURES = {
     "qz_rollout_finish": (C.c_int, [_vp, _i64, _vp, _i32, _i64, _u64, _u64, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
     "qz_mcts_backup_pending": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "qz_mcts_init": (C.c_int, [_vp, _vp, _vp, _vp]),
-    "qz_mcts_select": (C.c_int, [_vp, _f64, C.c_int, C.c_int, _vp, _vp]),
+    "qz_mcts_select": (C.c_int, [_vp, _f64, C.c_int, C.c_int, C.c_int, _vp, _vp]),
+    "qz_mcts_extend": (C.c_int, [_vp, _f64, _vp, _vp]),
     "qz_mcts_expand_backup": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _f64, C.c_int, _vp, _vp]),
     "qz_mcts_root_stats": (C.c_int, [_vp, _f64, _vp, _vp, _vp, _vp, _vp]),
     "qz_mcts_choose": (C.c_int, [_vp, C.c_int, _f64, _f64, _f64, _u64, _vp, _vp, _vp]),

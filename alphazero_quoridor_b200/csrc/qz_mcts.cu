@@ -158,7 +158,7 @@ extern "C" int qz_mcts_init(const qz_tree *tree, const qz_state *root_states, co
 // One warp per game; k_leaves sequential descents (virtual loss between them).
 #define QZ_SEL_MAX_CHILDREN 144        // a node has at most 140 children (12 pawn ids + 128 walls)
 template <bool UNIFORM_PRIOR>
-__global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, double c_puct, int k_leaves,
+__global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, double c_puct, int k_leaves, int lazy_expand,
                                                                 int32_t *__restrict__ overflow_count) {
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= t.n_games) return;
@@ -222,7 +222,12 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
         for (;;) {
             const bool at_root = depth == 0;
             int b = at_root ? rb : child_base[node];
-            if (b < 0) break;                                           // is_leaf (mcts.py:76)
+            if (b < 0) {                                                // is_leaf (mcts.py:76) -- or, with lazy expansion,
+                // a node that WAS expanded (visited) but whose legal mask has not been needed yet: qz_mcts_extend
+                // computes it now, builds the block and takes this descent one level further
+                if (UNIFORM_PRIOR && lazy_expand && !qz_done(s.meta) && visits[node] > 0) flags |= QZ_LEAF_NEEDS_MASK;
+                break;
+            }
             const int m = at_root ? rm : visits[b], total = at_root ? rtotal : visits[b + 2];
             const uint32_t pm = at_root ? rmeta + ((uint32_t)root_marks << 16) : meta[node];
             const int np_eff = (at_root ? rvis : visits[node]) + qz_meta_inflight(pm) - 1;  // minus this descent's own mark
@@ -361,17 +366,181 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
     if (lane == 0) t.n_nodes[g] = n_nodes;
 }
 
-extern "C" int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, int32_t *overflow_count,
-                              void *stream) {
+extern "C" int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, int lazy_expand,
+                              int32_t *overflow_count, void *stream) {
     int rc = qz_tree_check(tree, "qz_mcts_select");
     if (rc) return rc;
     QZ_REQUIRE(k_leaves >= 0 && k_leaves <= tree->leaves_per_game);
     if (!uniform_prior && tree->pool_cap <= 0) return qz_fail(QZ_E_NULL, "qz_mcts_select: stored priors need a prior pool");
     if (tree->n_games == 0) return 0;
     const unsigned blocks = qz_blocks_for(tree->n_games, 4);
-    if (uniform_prior) qz_mcts_select_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, k_leaves, overflow_count);
-    else qz_mcts_select_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, k_leaves, overflow_count);
+    QZ_REQUIRE(!lazy_expand || uniform_prior);
+    if (uniform_prior)
+        qz_mcts_select_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, k_leaves, lazy_expand, overflow_count);
+    else
+        qz_mcts_select_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, k_leaves, 0, overflow_count);
     return qz_check_launch("qz_mcts_select");
+}
+
+// ------------------------------------------------------------------------------------------ extend (lazy expansion)
+// Pure MCTS (uniform priors) never needs a node's legal actions until the node is visited a SECOND time: the first visit
+// only rolls out from it (pure_mcts.py:75-83 expands there and then, but the children it creates stay untouched until a
+// later playout descends through the node), and of a thousand playouts ~85 % end in a node that is never seen again
+// before the tree is thrown away (pure_mcts.py:142).  So with lazy_expand the 128-candidate legality sweep
+// (quoridor.py:420-528, the dearest thing a playout does after its rollout) is not run on every leaf: qz_mcts_select
+// stops at a visited node that has no block yet (QZ_LEAF_NEEDS_MASK), and this kernel -- one warp per game, its flagged
+// leaves in playout order -- computes that node's legal set, builds its block, and takes the descent one PUCT level
+// further (mcts.py:37-42,64-70), exactly what the eager form would have done from a block built at the first visit.
+__global__ void __launch_bounds__(128, 4) qz_mcts_extend_kernel(qz_tree t, double c_puct, int32_t *__restrict__ overflow_count) {
+    __shared__ uint32_t scratch[4][QZ_WARP_SCRATCH_WORDS];
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= t.n_games) return;
+    const int lane = threadIdx.x & 31;
+    const QzGameTree v = qz_game_tree(t, g);
+    float *__restrict__ prior = v.prior;
+    int32_t *__restrict__ visits = v.visits;
+    double *__restrict__ q = v.q;
+    int32_t *__restrict__ child_base = v.child_base;
+    uint32_t *__restrict__ meta = v.meta;
+    const int K = t.leaves_per_game;
+    const int root = t.root[g];
+    int n_nodes = t.n_nodes[g];
+    bool touched = false;
+    for (int k = 0; k < K; k++) {
+        const int64_t L = g * K + k;
+        unsigned flags = t.leaf_flags[L];
+        if (!(flags & QZ_LEAF_NEEDS_MASK)) continue;
+        flags &= ~QZ_LEAF_NEEDS_MASK;
+        touched = true;
+        const int X = qz_resolve(child_base, t.leaf_node[L]);
+        QzState s = qz_load_state(t.leaf_state + L);
+        const int len = t.path_len[L];
+        int b = child_base[X];
+        uint32_t pawn; uint64_t hl, vl;
+        __syncwarp();
+        if (b < 0) {                                                    // first descent to come back to X: expand it now
+            qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);  // Quoridor.actions(), quoridor.py:138-157
+            const int cnt = qz_popc32(pawn) + qz_popc64(hl) + qz_popc64(vl);
+            const int cap = X == root ? cnt : min(cnt, QZ_CAP0);
+            if (cnt == 0 || n_nodes + QZ_HDR + cap > t.node_cap) {
+                // no legal action (stalemate: the leaf stays X) or no room (counted; the playout is evaluated at X)
+                if (cnt != 0) { flags |= QZ_LEAF_ARENA_OVERFLOW; if (lane == 0 && overflow_count) atomicAdd(overflow_count, 1); }
+                if (lane == 0) t.leaf_flags[L] = (uint8_t)flags;
+                continue;
+            }
+            b = n_nodes;
+            n_nodes += QZ_HDR + cap;
+            uint64_t mk[3];
+            qz_pack_mask(pawn, hl, vl, mk);
+            if (lane < QZ_HDR) {
+                q[b + lane] = __longlong_as_double((long long)(lane == 0 ? mk[0] : (lane == 1 ? mk[1] : mk[2])));
+                meta[b + lane] = 0; prior[b + lane] = 0.0f;
+                visits[b + lane] = lane == 0 ? 0 : (lane == 1 ? cap : cnt);
+                child_base[b + lane] = lane == 2 ? 0 : -1;
+            }
+            __syncwarp();
+            if (lane == 0) child_base[X] = b;
+            __syncwarp();
+        } else {
+            qz_header_mask(v, b, pawn, hl, vl);
+        }
+        // one level of TreeNode.select (mcts.py:37-42) at X under uniform priors
+        const int m = visits[b], total = visits[b + 2];
+        const uint32_t pm = meta[X];
+        const int np_eff = visits[X] + qz_meta_inflight(pm) - 1;          // minus this descent's own mark
+        const double sq = sqrt((double)np_eff);
+        const double uni = c_puct * (1.0 / (double)total);               // pure_mcts.py:15
+        double best = -INFINITY;
+        int brank = 0x7FFFFFFF, bj = -1;
+        for (int j = lane; j < m; j += 32) {
+            const int c = b + QZ_HDR + j;
+            const uint32_t cm = meta[c];
+            const int n = visits[c], infl = qz_meta_inflight(cm);
+            double qv = q[c];
+            if (infl > 0) {
+                const double num = qv * (double)n - (double)infl;
+                qv = num == 0.0 ? 0.0 : num / (double)(n + infl);
+            }
+            const double val = qv + uni * sq / (double)(1 + n + infl);
+            const int rank = qz_meta_rank(cm);
+            if (val > best || (val == best && rank < brank)) { best = val; brank = rank; bj = j; }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const double ob = __shfl_xor_sync(QZ_FULL_MASK, best, off);
+            const int orank = __shfl_xor_sync(QZ_FULL_MASK, brank, off), oj = __shfl_xor_sync(QZ_FULL_MASK, bj, off);
+            if (oj >= 0 && (bj < 0 || ob > best || (ob == best && orank < brank))) { best = ob; brank = orank; bj = oj; }
+        }
+        bool take_new = false;
+        if (m < total) {
+            const double u0 = uni * sq / (double)(1 + 0 + 0);
+            take_new = bj < 0 || u0 > best || (u0 == best && m < brank);
+        }
+        int child = -1, act = -1;
+        if (take_new) {
+            act = qz_action_of_rank(pawn, hl, vl, m);
+            bool room = true;
+            if (m == visits[b + 1]) {                                   // block full: move it (see qz_mcts_select_kernel)
+                const int newcap = min(total, max(2 * m, QZ_CAP0));
+                if (n_nodes + QZ_HDR + newcap <= t.node_cap) {
+                    const int nb = n_nodes;
+                    n_nodes += QZ_HDR + newcap;
+                    for (int j = lane; j < QZ_HDR + m; j += 32) {
+                        prior[nb + j] = prior[b + j]; visits[nb + j] = visits[b + j]; q[nb + j] = q[b + j];
+                        child_base[nb + j] = child_base[b + j]; meta[nb + j] = meta[b + j];
+                    }
+                    __syncwarp();
+                    for (int j = lane; j < m; j += 32) child_base[b + QZ_HDR + j] = -2 - (nb + QZ_HDR + j);
+                    if (lane == 0) { visits[nb + 1] = newcap; child_base[X] = nb; }
+                    __syncwarp();
+                    b = nb;
+                } else {
+                    room = false;
+                    if (lane == 0 && overflow_count) atomicAdd(overflow_count, 1);
+                }
+            }
+            if (room) {
+                child = b + QZ_HDR + m;
+                if (lane == 0) {
+                    prior[child] = 1.0f / (float)total; visits[child] = 0; q[child] = 0.0; child_base[child] = -1;
+                    meta[child] = (uint32_t)act | ((uint32_t)m << 8) | (1u << 16);
+                    visits[b] = m + 1;
+                }
+            } else if (bj < 0) {
+                flags |= QZ_LEAF_ARENA_OVERFLOW;                        // nowhere to go: the playout is evaluated at X
+                if (lane == 0) t.leaf_flags[L] = (uint8_t)flags;
+                __syncwarp();
+                continue;
+            }
+        }
+        if (child < 0) {                                                // an existing child
+            if (bj < 0) bj = 0;
+            child = b + QZ_HDR + bj;
+            const uint32_t cm = meta[child];
+            act = qz_meta_action(cm);
+            __syncwarp();
+            if (lane == 0) meta[child] = cm + (1u << 16);
+        }
+        s = qz_apply(s, act);                                            // game.step(action), mcts.py:113
+        if (qz_done(s.meta)) flags |= QZ_LEAF_TERMINAL;
+        if (len + 1 >= t.max_depth) flags |= QZ_LEAF_DEPTH_OVERFLOW;
+        if (lane == 0) {
+            if (len < t.max_depth) { t.path[L * t.max_depth + len] = child; t.path_len[L] = len + 1; }
+            t.leaf_node[L] = child;
+            t.leaf_flags[L] = (uint8_t)flags;
+            qz_store_state(t.leaf_state + L, s);
+        }
+        __syncwarp();
+    }
+    if (touched && lane == 0) t.n_nodes[g] = n_nodes;
+}
+
+extern "C" int qz_mcts_extend(const qz_tree *tree, double c_puct, int32_t *overflow_count, void *stream) {
+    int rc = qz_tree_check(tree, "qz_mcts_extend");
+    if (rc) return rc;
+    if (tree->n_games == 0) return 0;
+    qz_mcts_extend_kernel<<<qz_blocks_for(tree->n_games, 4), 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, overflow_count);
+    return qz_check_launch("qz_mcts_extend");
 }
 
 // ------------------------------------------------------------------------------------------ expand + backup
@@ -379,7 +548,7 @@ extern "C" int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_pr
 // probs[legal], NOT renormalised), then update_recursive(-leaf_value) (mcts.py:44-62,127).
 // One warp per game, its leaves in order, so a game's tree is only ever touched by one warp: no atomics.
 struct QzExpandArgs {
-    const uint64_t *mask3;      // [n*K,3] legal masks of the leaves (qz_env_legal_mask on leaf_state)
+    const uint64_t *mask3;      // [n*K,3] legal masks of the leaves (qz_env_legal_mask on leaf_state); NULL = lazy expansion
     const float *priors;        // [n*K,140] or NULL (uniform 1/len, pure_mcts.py:13-16)
     const float *value_f32;     // [n*K] leaf value for the side to move (net), or NULL
     const double *value_f64;    // [n*K] same in float64 (stubs), or NULL
@@ -419,7 +588,7 @@ __global__ void __launch_bounds__(128) qz_mcts_expand_backup_kernel(qz_tree t, Q
             // a rollout still running in the deferred pass: expand now, back up later (qz_mcts_backup_pending);
             // the path keeps its in-flight marks meanwhile
             pending = a.value_i8 && a.value_i8[L] == (int8_t)QZ_ROLLOUT_PENDING;
-            if (node_cb < 0 && !(flags & (QZ_LEAF_DEPTH_OVERFLOW | QZ_LEAF_ARENA_OVERFLOW))) {
+            if (a.mask3 != nullptr && node_cb < 0 && !(flags & (QZ_LEAF_DEPTH_OVERFLOW | QZ_LEAF_ARENA_OVERFLOW))) {
                 uint32_t pawn; uint64_t hl, vl;
                 const uint64_t mk[3] = {a.mask3[3 * L], a.mask3[3 * L + 1], a.mask3[3 * L + 2]};
                 qz_unpack_mask(mk, pawn, hl, vl);
@@ -501,7 +670,7 @@ extern "C" int qz_mcts_expand_backup(const qz_tree *tree, const uint64_t *mask3,
                                      double c_puct, int fix_terminal_sign, int32_t *overflow_count, void *stream) {
     int rc = qz_tree_check(tree, "qz_mcts_expand_backup");
     if (rc) return rc;
-    QZ_REQUIRE_PTR(mask3);
+    if (mask3 == nullptr && priors != nullptr) return qz_fail(QZ_E_NULL, "qz_mcts_expand_backup: priors without legal masks");
     if (!value_f32 && !value_f64 && !value_i8) return qz_fail(QZ_E_NULL, "qz_mcts_expand_backup: no value array");
     if (priors && tree->pool_cap <= 0) return qz_fail(QZ_E_NULL, "qz_mcts_expand_backup: priors need a prior pool");
     if (tree->n_games == 0) return 0;

@@ -171,7 +171,7 @@ class NetEvaluator:
 class BatchedMCTS:
     def __init__(self, n_games, evaluator, c_puct=5, n_playout=100, leaves_per_game=1, node_cap=None,
                  max_depth=128, fix_terminal_sign=False, reuse_tree=True, device=None, defer_depth=0,
-                 defer_until_drain=False, allow_large_k=False, reuse_factor=4):
+                 defer_until_drain=False, allow_large_k=False, reuse_factor=4, lazy_expand=True):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda")
@@ -192,6 +192,8 @@ class BatchedMCTS:
                              "(pass allow_large_k=True to override)" % (self.K, MAX_K_NONUNIFORM))
         self.fix_terminal_sign = bool(fix_terminal_sign)
         self.max_depth = int(max_depth)
+        # uniform priors (pure MCTS): expand a node when a playout comes BACK to it, not when it is first reached
+        self.lazy_expand = self.uniform_prior and bool(lazy_expand)
         # playouts whose nodes one arena may have to hold: one search, or -- with tree reuse -- this move's playouts plus
         # the subtree kept from the moves before.  The reference keeps that subtree without bound (mcts.py:146-151); in
         # forced late-game lines a search keeps most of itself (the recorded reference runs reach 3.5 x n_playout kept
@@ -376,13 +378,19 @@ class BatchedMCTS:
                 self.cur_set = self.wave_index % len(self.sets)
                 self._settle(self.cur_set)          # the wave that used this leaf set defer_depth waves ago
             ls = self.sets[self.cur_set]
-            _lib.check(self.lib.qz_mcts_select(C.byref(self.tree), self.c_puct, int(self.uniform_prior), k,
+            lazy = self.lazy_expand
+            _lib.check(self.lib.qz_mcts_select(C.byref(self.tree), self.c_puct, int(self.uniform_prior), k, int(lazy),
                                                _lib.ptr(self.overflow), st), "qz_mcts_select")
             m = self.n * self.K
+            if lazy:
+                # uniform priors: a leaf's legal actions are only computed when a later playout comes back to it
+                _lib.check(self.lib.qz_mcts_extend(C.byref(self.tree), self.c_puct, _lib.ptr(self.overflow), st),
+                           "qz_mcts_extend")
+            else:
+                _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_mask), m, st),
+                           "qz_env_legal_mask")
             if self.count_tree_steps:
                 self.tree_steps += (ls.path_len.clamp(min=1) - 1).sum()
-            _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_mask), m, st),
-                       "qz_env_legal_mask")
             # rollout / RNG stream of leaf (g,k): (game id, playout counter) in separate bit fields, so two games can
             # never share a stream (pure_mcts.py:86-108 draws fresh randomness for every rollout)
             rids = None
@@ -396,7 +404,7 @@ class BatchedMCTS:
             else:
                 ev = self.evaluator.evaluate(self, ls, rids)
             _lib.check(self.lib.qz_mcts_expand_backup(
-                C.byref(self.tree), _lib.ptr(ls.leaf_mask), _lib.ptr(ev.get("priors")),
+                C.byref(self.tree), None if lazy else _lib.ptr(ls.leaf_mask), _lib.ptr(ev.get("priors")),
                 _lib.ptr(ev.get("value_f32")), _lib.ptr(ev.get("value_f64")), _lib.ptr(ev.get("value_i8")),
                 self.c_puct, int(self.fix_terminal_sign), _lib.ptr(self.overflow), st), "qz_mcts_expand_backup")
             if defer and not self.defer_until_drain:

@@ -220,6 +220,7 @@ typedef struct qz_tree {
 #define QZ_LEAF_DUPLICATE 0x08      /* another leaf of the same wave expanded this node first */
 #define QZ_LEAF_INACTIVE 0x10       /* slot k >= k_leaves of this wave */
 #define QZ_LEAF_PENDING 0x20        /* value was QZ_ROLLOUT_PENDING: expanded, backup owed (qz_mcts_backup_pending) */
+#define QZ_LEAF_NEEDS_MASK 0x40     /* lazy expansion: the descent stopped at a visited node without a block (qz_mcts_extend) */
 
 /* MCTS.__init__ (mcts.py:89-100) / update_with_move(-1) (:150-151): fresh root (prior 1.0) for every game
  * (or only those with select[g] != 0); root_states (nullable) are copied into tree->root_state. */
@@ -231,12 +232,21 @@ int qz_mcts_init(const qz_tree *tree, const qz_state *root_states, const uint8_t
  * uniform_prior != 0: priors are 1/len(children) in float64 (pure_mcts.py:13-16) instead of the stored f32.
  * With k_leaves > 1 later descents see a virtual loss on earlier paths (deviation; k_leaves = 1 is exact).
  * A child picked for the first time gets its slot here (overflow_count, nullable, counts the slots that did not fit). */
-int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, int32_t *overflow_count,
-                   void *stream);
+int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, int lazy_expand,
+                   int32_t *overflow_count, void *stream);
+
+/* Lazy expansion (uniform priors only; lazy_expand != 0 above and mask3 == NULL below).  pure_mcts.py:75-83 expands a leaf
+ * at its first visit, but nothing reads the children until a later playout comes back to the node -- and most leaves of a
+ * pure-MCTS search are never visited again.  With lazy_expand the descent stops at a visited node that has no block yet
+ * (QZ_LEAF_NEEDS_MASK) and this call computes that node's legal actions (Quoridor.actions, quoridor.py:138-157), builds
+ * the block and takes the descent one more PUCT level (mcts.py:37-42), leaving leaf_node / leaf_state / path as the
+ * eager form would.  Same visit counts as the eager form at k_leaves = 1. */
+int qz_mcts_extend(const qz_tree *tree, double c_puct, int32_t *overflow_count, void *stream);
 
 /* The rest of MCTS._playout (mcts.py:117-127): for every leaf of the last select, unless terminal, expand
  * with (action, prior) over the legal actions in actions() order (TreeNode.expand, mcts.py:27-35; priors
- * [n*K,140] are read at the legal actions only and NOT renormalised, policy_value_net.py:162; NULL = uniform)
+ * [n*K,140] are read at the legal actions only and NOT renormalised, policy_value_net.py:162; NULL = uniform;
+ * mask3 == NULL with priors == NULL = lazy expansion: nothing is expanded here, see qz_mcts_extend)
  * and back up -leaf_value along the path with a sign flip per level (update_recursive, mcts.py:44-62).
  * Exactly one of value_f32 / value_f64 / value_i8 is the evaluator's value for the side to move.  Terminal
  * leaves use +1 (the reference's inverted sign, mcts.py:125) or -1 when fix_terminal_sign != 0. */

@@ -83,11 +83,11 @@ def test_more_argument_errors_need_no_gpu(so_path):
     # trees
     t = tree.QzTree()
     assert lib.qz_mcts_init(None, None, None, None) == -1
-    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, None, None) == -2                                      # zero dimensions
+    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, 0, None, None) == -2                                      # zero dimensions
     t.n_games, t.node_cap, t.max_depth, t.leaves_per_game = 4, 100, 16, 2
-    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, None, None) == -2                                      # node_cap < one full block
+    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, 0, None, None) == -2                                      # node_cap < one full block
     t.node_cap = 1000
-    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, None, None) == -1                                      # arrays NULL
+    assert lib.qz_mcts_select(C.byref(t), 5.0, 0, 1, 0, None, None) == -1                                      # arrays NULL
     assert b"NULL" in lib.qz_last_error_string()
     assert lib.qz_stub_eval(p8, p8, 9, p8, p8, 4, None) == -2                                                # unknown stub kind
     assert lib.qz_device_sm_count(None) == -1

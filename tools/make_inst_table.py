@@ -73,7 +73,9 @@ def main():
     args = bench.parse([])
     os.makedirs(os.path.dirname(a.csv), exist_ok=True)
     if not a.parse_only:
-        cmd = ["ncu", "--profile-from-start", "off", "--clock-control", "none", "--metrics", ",".join(METRICS), "--csv",
+        # -k regex:qz_ : only the library's own kernels (a torch elementwise kernel once failed to profile and took the
+        # whole capture down; torch's share of the step is < 0.1 % of the instructions)
+        cmd = ["ncu", "--profile-from-start", "off", "--clock-control", "none", "-k", "regex:qz_", "--metrics", ",".join(METRICS), "--csv",
                "--log-file", a.csv, sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(a.plies), "--warmup", "0",
                "--ncu-range", "--no-kernels", "--no-az", "--no-parity", "--no-cpu-baseline", "--games-plies", "0"]
         print(" ".join(cmd), flush=True)
