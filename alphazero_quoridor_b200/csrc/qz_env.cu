@@ -75,6 +75,39 @@ __global__ void __launch_bounds__(128, 4) qz_legal_mask_kernel(const qz_state *_
     }
 }
 
+// The same sweep for the flagged positions only (lazy expansion, qz_mcts_extend: the leaves whose descent stopped at a
+// node that needs its legal set now); the masks of the others are left untouched.
+__global__ void __launch_bounds__(128, 4) qz_legal_mask_flagged_kernel(const qz_state *__restrict__ states,
+                                                                    const uint8_t *__restrict__ flags, int flag_bits,
+                                                                    uint64_t *__restrict__ mask3, int64_t n) {
+    __shared__ uint32_t scratch[4][QZ_WARP_SCRATCH_WORDS];
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= n) return;
+    if (!(flags[g] & flag_bits)) return;
+    const QzState s = qz_load_state(states + g);
+    uint32_t pawn; uint64_t hl, vl;
+    qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);
+    const int lane = threadIdx.x & 31;
+    if (lane < 3) {
+        uint64_t out[3];
+        qz_pack_mask(pawn, hl, vl, out);
+        mask3[3 * g + lane] = lane == 0 ? out[0] : (lane == 1 ? out[1] : out[2]);
+    }
+}
+
+extern "C" int qz_env_legal_mask_flagged(const qz_state *states, const uint8_t *flags, int flag_bits, uint64_t *mask3,
+                                         int64_t n, void *stream) {
+    QZ_REQUIRE(n >= 0);
+    if (n == 0) return 0;
+    QZ_REQUIRE_PTR(states);
+    QZ_REQUIRE_PTR(flags);
+    QZ_REQUIRE_PTR(mask3);
+    QZ_REQUIRE_ALIGN(states, 8);
+    QZ_REQUIRE_ALIGN(mask3, 8);
+    qz_legal_mask_flagged_kernel<<<qz_blocks_for(n, 4), 128, 0, (cudaStream_t)stream>>>(states, flags, flag_bits, mask3, n);
+    return qz_check_launch("qz_env_legal_mask_flagged");
+}
+
 extern "C" int qz_env_legal_mask(const qz_state *states, uint64_t *mask3, int64_t n, void *stream) {
     QZ_REQUIRE(n >= 0);
     if (n == 0) return 0;

@@ -39,6 +39,10 @@
 
 #define QZ_HDR 3                       // header slots of a block
 #define QZ_CAP0 4                      // initial capacity of a non-root block
+// child_base of a slot: >= 0 its block; -1 never evaluated (is_leaf()); QZ_CB_LAZY evaluated once -- the reference
+// expanded it then (pure_mcts.py:77-79) -- but its block is only built when a playout comes back (lazy expansion);
+// -2 - x (x < node_cap) moved to slot x
+#define QZ_CB_LAZY ((int32_t)0x80000000)
 
 __device__ __forceinline__ int qz_meta_action(uint32_t m) { return (int)(m & 0xFFu); }
 __device__ __forceinline__ int qz_meta_rank(uint32_t m) { return (int)((m >> 8) & 0xFFu); }
@@ -69,7 +73,7 @@ __device__ __forceinline__ QzGameTree qz_game_tree(const qz_tree &t, int64_t g) 
 // follow the forwarding indices a relocated block left behind
 __device__ __forceinline__ int qz_resolve(const int32_t *child_base, int i) {
     int cb;
-    while ((cb = child_base[i]) <= -2) i = -2 - cb;
+    while ((cb = child_base[i]) <= -2 && cb != QZ_CB_LAZY) i = -2 - cb;
     return i;
 }
 __device__ __forceinline__ void qz_header_mask(const QzGameTree &v, int b, uint32_t &pawn, uint64_t &hl, uint64_t &vl) {
@@ -223,9 +227,9 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
             const bool at_root = depth == 0;
             int b = at_root ? rb : child_base[node];
             if (b < 0) {                                                // is_leaf (mcts.py:76) -- or, with lazy expansion,
-                // a node that WAS expanded (visited) but whose legal mask has not been needed yet: qz_mcts_extend
-                // computes it now, builds the block and takes this descent one level further
-                if (UNIFORM_PRIOR && lazy_expand && !qz_done(s.meta) && visits[node] > 0) flags |= QZ_LEAF_NEEDS_MASK;
+                // a node that WAS expanded (evaluated before) but whose legal mask has not been needed yet:
+                // qz_mcts_extend builds the block from the mask and takes this descent one level further
+                if (UNIFORM_PRIOR && lazy_expand && b == QZ_CB_LAZY && !qz_done(s.meta)) flags |= QZ_LEAF_NEEDS_MASK;
                 break;
             }
             const int m = at_root ? rm : visits[b], total = at_root ? rtotal : visits[b + 2];
@@ -391,7 +395,8 @@ extern "C" int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_pr
 // stops at a visited node that has no block yet (QZ_LEAF_NEEDS_MASK), and this kernel -- one warp per game, its flagged
 // leaves in playout order -- computes that node's legal set, builds its block, and takes the descent one PUCT level
 // further (mcts.py:37-42,64-70), exactly what the eager form would have done from a block built at the first visit.
-__global__ void __launch_bounds__(128, 4) qz_mcts_extend_kernel(qz_tree t, double c_puct, int32_t *__restrict__ overflow_count) {
+__global__ void __launch_bounds__(128, 4) qz_mcts_extend_kernel(qz_tree t, double c_puct, const uint64_t *__restrict__ mask3,
+                                                                int32_t *__restrict__ overflow_count) {
     __shared__ uint32_t scratch[4][QZ_WARP_SCRATCH_WORDS];
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= t.n_games) return;
@@ -419,7 +424,12 @@ __global__ void __launch_bounds__(128, 4) qz_mcts_extend_kernel(qz_tree t, doubl
         uint32_t pawn; uint64_t hl, vl;
         __syncwarp();
         if (b < 0) {                                                    // first descent to come back to X: expand it now
-            qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);  // Quoridor.actions(), quoridor.py:138-157
+            if (mask3 != nullptr) {                                     // swept in parallel by qz_env_legal_mask_flagged
+                const uint64_t mk[3] = {mask3[3 * L], mask3[3 * L + 1], mask3[3 * L + 2]};
+                qz_unpack_mask(mk, pawn, hl, vl);
+            } else {
+                qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);  // Quoridor.actions(), quoridor.py:138-157
+            }
             const int cnt = qz_popc32(pawn) + qz_popc64(hl) + qz_popc64(vl);
             const int cap = X == root ? cnt : min(cnt, QZ_CAP0);
             if (cnt == 0 || n_nodes + QZ_HDR + cap > t.node_cap) {
@@ -535,11 +545,45 @@ __global__ void __launch_bounds__(128, 4) qz_mcts_extend_kernel(qz_tree t, doubl
     if (touched && lane == 0) t.n_nodes[g] = n_nodes;
 }
 
-extern "C" int qz_mcts_extend(const qz_tree *tree, double c_puct, int32_t *overflow_count, void *stream) {
+// End of a lazily expanded search: a root that was evaluated but never came back to (n_playout = 1) gets its block, so
+// that root statistics and the move choice see its children (all unvisited) as the reference's would.
+__global__ void __launch_bounds__(128, 4) qz_mcts_build_root_kernel(qz_tree t, int32_t *__restrict__ overflow_count) {
+    __shared__ uint32_t scratch[4][QZ_WARP_SCRATCH_WORDS];
+    const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (g >= t.n_games) return;
+    const int lane = threadIdx.x & 31;
+    const QzGameTree v = qz_game_tree(t, g);
+    const int root = t.root[g];
+    if (v.child_base[root] != QZ_CB_LAZY) return;
+    const QzState s = qz_load_state(t.root_state + g);
+    uint32_t pawn; uint64_t hl, vl;
+    qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);
+    const int cnt = qz_popc32(pawn) + qz_popc64(hl) + qz_popc64(vl);
+    const int n_nodes = t.n_nodes[g];
+    if (cnt == 0) return;
+    if (n_nodes + QZ_HDR + cnt > t.node_cap) { if (lane == 0 && overflow_count) atomicAdd(overflow_count, 1); return; }
+    const int b = n_nodes;
+    uint64_t mk[3];
+    qz_pack_mask(pawn, hl, vl, mk);
+    if (lane < QZ_HDR) {
+        v.q[b + lane] = __longlong_as_double((long long)(lane == 0 ? mk[0] : (lane == 1 ? mk[1] : mk[2])));
+        v.meta[b + lane] = 0; v.prior[b + lane] = 0.0f;
+        v.visits[b + lane] = lane == 0 ? 0 : cnt;
+        v.child_base[b + lane] = lane == 2 ? 0 : -1;
+    }
+    __syncwarp();
+    if (lane == 0) { v.child_base[root] = b; t.n_nodes[g] = n_nodes + QZ_HDR + cnt; }
+}
+
+extern "C" int qz_mcts_extend(const qz_tree *tree, double c_puct, const uint64_t *mask3, int root_only, int32_t *overflow_count,
+                              void *stream) {
     int rc = qz_tree_check(tree, "qz_mcts_extend");
     if (rc) return rc;
     if (tree->n_games == 0) return 0;
-    qz_mcts_extend_kernel<<<qz_blocks_for(tree->n_games, 4), 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, overflow_count);
+    if (root_only)
+        qz_mcts_build_root_kernel<<<qz_blocks_for(tree->n_games, 4), 128, 0, (cudaStream_t)stream>>>(*tree, overflow_count);
+    else
+        qz_mcts_extend_kernel<<<qz_blocks_for(tree->n_games, 4), 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, mask3, overflow_count);
     return qz_check_launch("qz_mcts_extend");
 }
 
@@ -629,6 +673,10 @@ __global__ void __launch_bounds__(128) qz_mcts_expand_backup_kernel(qz_tree t, Q
                         if (lane == 0 && a.overflow_count) atomicAdd(a.overflow_count, 1);
                     }
                 }
+            } else if (a.mask3 == nullptr && node_cb == -1 && !(flags & QZ_LEAF_DEPTH_OVERFLOW)) {
+                // lazy expansion: remember that the reference expanded this node now; its block comes when needed
+                __syncwarp();
+                if (lane == 0) child_base[node] = QZ_CB_LAZY;
             } else if (node_cb >= 0) {
                 flags |= QZ_LEAF_DUPLICATE;
             }
@@ -997,7 +1045,8 @@ __global__ void __launch_bounds__(128) qz_mcts_reroot_kernel(qz_tree src, qz_tre
         dv.visits[0] = sv.visits[found];
         dv.q[0] = sv.q[found];
         dv.meta[0] = sv.meta[found] & 0x0000FFFFu;                      // drop stale in-flight marks
-        dv.child_base[0] = sv.child_base[found] >= 0 ? sv.child_base[found] : -1;   // src block, pending
+        const int fcb = sv.child_base[found];
+        dv.child_base[0] = fcb >= 0 ? fcb : (fcb == QZ_CB_LAZY ? QZ_CB_LAZY : -1);  // >= 0: src block, pending
     }
     __syncwarp();
     // breadth first over BLOCKS: the root slot first, then the child slots of every block in the order the blocks were
@@ -1047,7 +1096,7 @@ __global__ void __launch_bounds__(128) qz_mcts_reroot_kernel(qz_tree src, qz_tre
                     dv.q[dc] = sv.q[sc];
                     dv.meta[dc] = sv.meta[sc] & 0x0000FFFFu;
                     const int scb = sv.child_base[sc];
-                    dv.child_base[dc] = scb >= 0 ? scb : -1;
+                    dv.child_base[dc] = scb >= 0 ? scb : (scb == QZ_CB_LAZY ? QZ_CB_LAZY : -1);
                 }
                 __syncwarp();
                 if (lane == 0) dv.child_base[slot] = db;

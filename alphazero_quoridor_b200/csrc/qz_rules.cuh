@@ -516,6 +516,19 @@ QZ_HD uint32_t qz_goal_hit(const BB &r, int player) { return player == 1 ? (r.w2
 // Continue a search whose plain-move closure `reach` (a fixpoint that misses the goal row) is known: apply the
 // jump edges, re-close, repeat.  The jump set is built here, lazily (see qz_reaches_goal).
 QZ_HD bool qz_reach_with_jumps(const QzDirs &d, BB reach, int O, int player, uint64_t H, uint64_t V) {
+    // A jump edge leaves one of the four tiles next to the opponent (raw offsets, quoridor.py:278-281).  `reach` is closed
+    // under plain moves and plain moves add nothing next to the opponent later, so if none of those tiles is in it no
+    // jump can ever be taken: the answer is "no" without building the jump set (a corner-mask rebuild, ~600
+    // instructions -- and in blocked positions nearly every check ends here).
+    {
+        BB src = bb_zero();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int t = qz_jump_src(O, i);
+            if ((unsigned)t <= 80u) src = bb_or(src, bb_bit(t));
+        }
+        if (!bb_any(bb_and(reach, src))) return false;
+    }
     BB keep = bb_bit(O);
     keep.w0 = ~keep.w0; keep.w1 = ~keep.w1; keep.w2 = ~keep.w2;
     const uint32_t jumps = qz_jump_set_rebuilt(H, V, O, player);

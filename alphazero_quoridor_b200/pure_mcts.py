@@ -42,7 +42,7 @@ class MCTS(object):
         self._evaluator = _tree.RolloutEvaluator(seed=seed, limit=1000)
         self._engine = _tree.BatchedMCTS(1, self._evaluator, c_puct=c_puct, n_playout=n_playout,
                                          leaves_per_game=leaves_per_game, fix_terminal_sign=fix_terminal_sign,
-                                         reuse_tree=False, device=device)
+                                         reuse_tree=False, device=device, lazy_expand=False)   # `_children` right after a playout
         self._engine.reset(torch.tensor([Quoridor().packed()], dtype=torch.int64))
 
     @property

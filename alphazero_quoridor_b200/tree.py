@@ -20,6 +20,7 @@ from . import _lib
 from .rollout import rollout as _rollout
 
 LEAF_TERMINAL, LEAF_DEPTH_OVERFLOW, LEAF_ARENA_OVERFLOW, LEAF_DUPLICATE, LEAF_INACTIVE, LEAF_PENDING = 1, 2, 4, 8, 16, 32
+LEAF_NEEDS_MASK = 64
 MAX_CHILDREN = 140
 SLOTS_PER_PLAYOUT = 12                 # default arena slots per playout kept (see BatchedMCTS.__init__)
 MAX_K_NONUNIFORM = 8                   # leaves per game per wave allowed under non-uniform priors (see BatchedMCTS)
@@ -383,9 +384,13 @@ class BatchedMCTS:
                                                _lib.ptr(self.overflow), st), "qz_mcts_select")
             m = self.n * self.K
             if lazy:
-                # uniform priors: a leaf's legal actions are only computed when a later playout comes back to it
-                _lib.check(self.lib.qz_mcts_extend(C.byref(self.tree), self.c_puct, _lib.ptr(self.overflow), st),
-                           "qz_mcts_extend")
+                # uniform priors: a leaf's legal actions are only computed when a later playout comes back to it -- swept
+                # for the flagged leaves in parallel (a warp per leaf), then the block is built and the descent continued
+                _lib.check(self.lib.qz_env_legal_mask_flagged(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_flags),
+                                                              LEAF_NEEDS_MASK, _lib.ptr(ls.leaf_mask), m, st),
+                           "qz_env_legal_mask_flagged")
+                _lib.check(self.lib.qz_mcts_extend(C.byref(self.tree), self.c_puct, _lib.ptr(ls.leaf_mask), 0,
+                                                   _lib.ptr(self.overflow), st), "qz_mcts_extend")
             else:
                 _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_mask), m, st),
                            "qz_env_legal_mask")
@@ -425,6 +430,12 @@ class BatchedMCTS:
             self.playout_wave(k)
             done += k
         self.drain()
+        if self.lazy_expand:
+            # a root that was evaluated but never revisited (n_playout = 1) gets its block: its children are the
+            # reference's freshly expanded ones
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.qz_mcts_extend(C.byref(self.tree), self.c_puct, None, 1, _lib.ptr(self.overflow),
+                                                   self._stream()), "qz_mcts_extend")
 
     def root_stats(self, temp=1e-3, want_q=False):
         """(visits int32 [n,140], probs float64 [n,140], root_visits int32 [n][, q float64 [n,140]])

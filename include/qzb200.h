@@ -105,6 +105,11 @@ int qz_env_step(qz_state *states, const int32_t *actions, const uint64_t *legal_
  */
 int qz_env_legal_mask(const qz_state *states, uint64_t *mask3, int64_t n, void *stream);
 
+/* The same for the positions whose flags[i] & flag_bits != 0 only (the others' masks are left untouched): the lazily
+ * expanded search sweeps just the leaves that came back to a node (flags = qz_tree.leaf_flags, QZ_LEAF_NEEDS_MASK). */
+int qz_env_legal_mask_flagged(const qz_state *states, const uint8_t *flags, int flag_bits, uint64_t *mask3, int64_t n,
+                              void *stream);
+
 /*
  * The reference's random policy over the FULL legal set (pure_mcts.rollout_policy_fn, pure_mcts.py:7-10: argmax of
  * iid uniforms over actions() == one uniform legal action): actions[i] = the k-th set bit of game i's legal mask,
@@ -240,8 +245,12 @@ int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_
  * pure-MCTS search are never visited again.  With lazy_expand the descent stops at a visited node that has no block yet
  * (QZ_LEAF_NEEDS_MASK) and this call computes that node's legal actions (Quoridor.actions, quoridor.py:138-157), builds
  * the block and takes the descent one more PUCT level (mcts.py:37-42), leaving leaf_node / leaf_state / path as the
- * eager form would.  Same visit counts as the eager form at k_leaves = 1. */
-int qz_mcts_extend(const qz_tree *tree, double c_puct, int32_t *overflow_count, void *stream);
+ * eager form would.  Same visit counts as the eager form at k_leaves = 1.  mask3 (nullable): the legal masks of the flagged
+ * leaves computed beforehand by qz_env_legal_mask_flagged(leaf_state, leaf_flags, QZ_LEAF_NEEDS_MASK, ...) -- a warp per
+ * leaf instead of this kernel's warp per game; NULL = computed here.  root_only != 0: no descent; only gives a root that
+ * was evaluated but never revisited (n_playout = 1) its block, so that the statistics see its children. */
+int qz_mcts_extend(const qz_tree *tree, double c_puct, const uint64_t *mask3, int root_only, int32_t *overflow_count,
+                   void *stream);
 
 /* The rest of MCTS._playout (mcts.py:117-127): for every leaf of the last select, unless terminal, expand
  * with (action, prior) over the legal actions in actions() order (TreeNode.expand, mcts.py:27-35; priors

@@ -66,18 +66,22 @@ def parse_csv(path):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--plies", type=int, default=26)
+    ap.add_argument("--plies", default="0,3,5,8,11,14,17,20,23,25",
+                    help="self-play plies to capture (ncu costs ~0.15 s per launch, ~400 launches per ply); bench.py "
+                         "interpolates the plies in between")
     ap.add_argument("--csv", default=os.path.join(ROOT, "gpurun_out", "inst_table_launches.csv"))
     ap.add_argument("--parse-only", action="store_true")
     a = ap.parse_args()
     args = bench.parse([])
+    plies = sorted(int(x) for x in a.plies.split(",") if x.strip())
     os.makedirs(os.path.dirname(a.csv), exist_ok=True)
     if not a.parse_only:
         # -k regex:qz_ : only the library's own kernels (a torch elementwise kernel once failed to profile and took the
         # whole capture down; torch's share of the step is < 0.1 % of the instructions)
         cmd = ["ncu", "--profile-from-start", "off", "--clock-control", "none", "-k", "regex:qz_", "--metrics", ",".join(METRICS), "--csv",
-               "--log-file", a.csv, sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(a.plies), "--warmup", "0",
-               "--ncu-range", "--no-kernels", "--no-az", "--no-parity", "--no-cpu-baseline", "--games-plies", "0"]
+               "--log-file", a.csv, sys.executable, os.path.join(ROOT, "bench.py"), "--steps", str(max(plies) + 1), "--warmup", "0",
+               "--ncu-range", "--ncu-plies", a.plies, "--no-kernels", "--no-az", "--no-parity", "--no-cpu-baseline",
+               "--games-plies", "0"]
         print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd, stdout=subprocess.DEVNULL)
     rows = parse_csv(a.csv)
@@ -112,26 +116,30 @@ def main():
                 t[f] += v[f]
         for f in ("warp_inst", "thread_inst", "time_ms", "dram_bytes", "launches"):
             per_ply[-1][f] += cur[f]
+    if len(per_ply) != len(plies):
+        print("WARNING: captured %d plies, expected %d (%s): keeping the first ones" % (len(per_ply), len(plies), plies))
+    per_ply = {str(p): row for p, row in zip(plies, per_ply)}
     table = {"when": datetime.datetime.utcnow().isoformat() + "Z", "build_hash": bench.build_hash(),
              "args": {k: getattr(args, k) for k in ("games", "playouts", "leaves", "seed", "defer")},
              "metrics": METRICS, "how": "ncu --profile-from-start off --clock-control none, kernel replay; time_ms is "
-             "serialised and cold-cache (compare shares, not absolutes)", "plies": len(per_ply), "per_ply": per_ply}
+             "serialised and cold-cache (compare shares, not absolutes)", "plies": list(per_ply), "per_ply": per_ply}
     out = os.path.join(ROOT, "profiles", "inst_table.json")
     with open(out, "w") as f:
         json.dump(table, f, indent=0)
-    tot = sum(p["warp_inst"] for p in per_ply)
-    print("wrote %s: %d plies, %d launches, %.2f G warp instructions per ply (mean), %.1f lanes/instruction"
-          % (out, len(per_ply), sum(p["launches"] for p in per_ply), tot / max(len(per_ply), 1) / 1e9,
-             sum(p["thread_inst"] for p in per_ply) / max(tot, 1)))
+    rows_all = list(per_ply.values())
+    tot = sum(p["warp_inst"] for p in rows_all)
+    print("wrote %s: plies %s, %d launches, %.2f G warp instructions per ply (mean), %.1f lanes/instruction"
+          % (out, list(per_ply), sum(p["launches"] for p in rows_all), tot / max(len(rows_all), 1) / 1e9,
+             sum(p["thread_inst"] for p in rows_all) / max(tot, 1)))
     agg = {}
-    for p in per_ply:
+    for p in rows_all:
         for k, v in p["kernels"].items():
             g = agg.setdefault(k, {"launches": 0, "warp_inst": 0.0, "thread_inst": 0.0, "time_ms": 0.0})
             for f in g:
                 g[f] += v[f]
     tms = sum(v["time_ms"] for v in agg.values()) or 1.0
     with open(os.path.join(ROOT, "profiles", "inst_table_summary.txt"), "w") as f:
-        f.write("# %s  build %s  %d plies of `python bench.py` (ncu, serialised)\n" % (table["when"], table["build_hash"], len(per_ply)))
+        f.write("# %s  build %s  plies %s of `python bench.py` (ncu, serialised)\n" % (table["when"], table["build_hash"], list(per_ply)))
         f.write("%-36s %8s %14s %8s %8s %8s\n" % ("kernel", "launches", "warp_inst", "inst %", "time %", "lanes"))
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["warp_inst"]):
             f.write("%-36s %8d %14.4g %8.2f %8.2f %8.1f\n" % (k, v["launches"], v["warp_inst"], 100 * v["warp_inst"] / max(tot, 1),
