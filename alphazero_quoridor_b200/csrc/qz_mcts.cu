@@ -161,7 +161,13 @@ extern "C" int qz_mcts_init(const qz_tree *tree, const qz_state *root_states, co
 // ------------------------------------------------------------------------------------------ select
 // One warp per game; k_leaves sequential descents (virtual loss between them).
 #define QZ_SEL_MAX_CHILDREN 144        // a node has at most 140 children (12 pawn ids + 128 walls)
-template <bool UNIFORM_PRIOR>
+// FAST_ROOT (used when a wave collects more than one leaf per game): the k_leaves descents of a game re-evaluate all of the
+// root's children (up to 131) every time, two float64 divisions each; the root's per-child terms 1/(1+n+inflight) and the
+// virtual-loss value are therefore kept in shared memory, refreshed for the one child a descent picks, and a child's
+// value becomes one fused multiply-add.  Multiplying by a stored reciprocal is not bit-identical to the reference's
+// division (mcts.py:69), which only the one-leaf-per-wave search reproduces bit for bit anyway -- that search keeps the
+// literal arithmetic (FAST_ROOT = false).
+template <bool UNIFORM_PRIOR, bool FAST_ROOT>
 __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, double c_puct, int k_leaves, int lazy_expand,
                                                                 int32_t *__restrict__ overflow_count) {
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -185,6 +191,8 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
     __shared__ uint32_t s_meta[4][QZ_SEL_MAX_CHILDREN];
     __shared__ double s_q[4][QZ_SEL_MAX_CHILDREN];
     __shared__ float s_prior[UNIFORM_PRIOR ? 1 : 4][UNIFORM_PRIOR ? 1 : QZ_SEL_MAX_CHILDREN];
+    __shared__ double s_rcp[FAST_ROOT ? 4 : 1][FAST_ROOT ? QZ_SEL_MAX_CHILDREN : 1];    // 1 / (1 + n + inflight)
+    __shared__ double s_qv[FAST_ROOT ? 4 : 1][FAST_ROOT ? QZ_SEL_MAX_CHILDREN : 1];     // Q with the virtual loss applied
     const int wib = threadIdx.x >> 5;
     int rb = child_base[root];
     uint32_t rmeta = 0;
@@ -199,6 +207,12 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
             s_meta[wib][j] = meta[c];
             s_q[wib][j] = q[c];
             if (!UNIFORM_PRIOR) s_prior[wib][j] = prior[c];
+            if (FAST_ROOT) {
+                const int n = s_n[wib][j], infl = qz_meta_inflight(s_meta[wib][j]);
+                const double num = s_q[wib][j] * (double)n - (double)infl;
+                s_qv[wib][j] = infl > 0 ? (num == 0.0 ? 0.0 : num / (double)(n + infl)) : s_q[wib][j];
+                s_rcp[wib][j] = 1.0 / (double)(1 + n + infl);
+            }
         }
     }
     __syncwarp();
@@ -239,6 +253,14 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
             const double uni = UNIFORM_PRIOR ? c_puct * (1.0 / (double)total) : 0.0;   // pure_mcts.py:15
             double best = -INFINITY;
             int brank = 0x7FFFFFFF, bj = -1;
+            if (FAST_ROOT && at_root) {
+                for (int j = lane; j < m; j += 32) {
+                    const double cp = UNIFORM_PRIOR ? uni : (double)(c_puct_f * s_prior[wib][j]);
+                    const double val = fma(cp * sq, s_rcp[wib][j], s_qv[wib][j]);
+                    const int rank = qz_meta_rank(s_meta[wib][j]);
+                    if (val > best || (val == best && rank < brank)) { best = val; brank = rank; bj = j; }
+                }
+            } else
             for (int j = lane; j < m; j += 32) {
                 const int c = b + QZ_HDR + j;
                 const uint32_t cm = at_root ? s_meta[wib][j] : meta[c];
@@ -332,6 +354,7 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
                         if (lane == 0) {
                             s_n[wib][m] = 0; s_meta[wib][m] = cm; s_q[wib][m] = 0.0;
                             if (!UNIFORM_PRIOR) s_prior[wib][m] = uprior;
+                            if (FAST_ROOT) { s_qv[wib][m] = -1.0; s_rcp[wib][m] = 0.5; }   // n = 0, one mark: -1/1, 1/(1+0+1)
                         }
                         rm = m + 1;
                     }
@@ -353,7 +376,15 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
             if (lane == 0) {
                 path[depth] = node;
                 meta[node] = cm + (1u << 16);
-                if (at_root) s_meta[wib][bj] = cm + (1u << 16);
+                if (at_root) {
+                    s_meta[wib][bj] = cm + (1u << 16);
+                    if (FAST_ROOT) {
+                        const int n = s_n[wib][bj], infl = qz_meta_inflight(cm) + 1;
+                        const double num = s_q[wib][bj] * (double)n - (double)infl;
+                        s_qv[wib][bj] = num == 0.0 ? 0.0 : num / (double)(n + infl);
+                        s_rcp[wib][bj] = 1.0 / (double)(1 + n + infl);
+                    }
+                }
             }
             __syncwarp();
             if (depth >= t.max_depth - 1) { flags |= QZ_LEAF_DEPTH_OVERFLOW; break; }
@@ -379,10 +410,12 @@ extern "C" int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_pr
     if (tree->n_games == 0) return 0;
     const unsigned blocks = qz_blocks_for(tree->n_games, 4);
     QZ_REQUIRE(!lazy_expand || uniform_prior);
-    if (uniform_prior)
-        qz_mcts_select_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, k_leaves, lazy_expand, overflow_count);
-    else
-        qz_mcts_select_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(*tree, c_puct, k_leaves, 0, overflow_count);
+    const bool fast = tree->leaves_per_game > 1;      // one leaf per wave = the reference's arithmetic, literally
+    cudaStream_t st = (cudaStream_t)stream;
+    if (uniform_prior && fast) qz_mcts_select_kernel<true, true><<<blocks, 128, 0, st>>>(*tree, c_puct, k_leaves, lazy_expand, overflow_count);
+    else if (uniform_prior) qz_mcts_select_kernel<true, false><<<blocks, 128, 0, st>>>(*tree, c_puct, k_leaves, lazy_expand, overflow_count);
+    else if (fast) qz_mcts_select_kernel<false, true><<<blocks, 128, 0, st>>>(*tree, c_puct, k_leaves, 0, overflow_count);
+    else qz_mcts_select_kernel<false, false><<<blocks, 128, 0, st>>>(*tree, c_puct, k_leaves, 0, overflow_count);
     return qz_check_launch("qz_mcts_select");
 }
 
