@@ -10,6 +10,8 @@
 // first capture (profiles/r1a_rollout_ncu_full.txt) of the single-kernel form showed 4.2 active lanes per
 // instruction because a warp mixed both kinds.  No tensor cores: the game lives in registers (the pawn phase
 // adds a byte-per-tile table in shared memory) and HBM sees 24 B in, 48 B through `mid`, 1..29 B out per ROLLOUT.
+#include <stdlib.h>
+
 #include "qz_common.cuh"
 #include "qz_sample.cuh"
 #include "qz_warp.cuh"
@@ -151,7 +153,10 @@ struct QzStuckSmem {                   // one per warp
     uint64_t ki_h[QZ_MEMO_SLOTS], ki_v[QZ_MEMO_SLOTS];   // known blocking
 };
 
-__global__ void __launch_bounds__(128, 4) qz_rollout_stuck_kernel(QzRolloutArgs a) {
+// MIN_BLOCKS = resident one-warp blocks per SM the register budget is cut for (16 -> 128 registers, 20 -> 96, 24 -> 80):
+// the pass is latency-bound with one warp per rollout, so residency is throughput as long as the spills stay small.
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(QZ_STUCK_THREADS, MIN_BLOCKS) qz_rollout_stuck_kernel(QzRolloutArgs a) {
     __shared__ QzStuckSmem s_all[QZ_STUCK_THREADS / 32];
     QzStuckSmem &sm = s_all[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -534,6 +539,23 @@ static int qz_pawn_passes(QzRolloutArgs a, bool finish, cudaStream_t st, const c
     return 0;
 }
 
+// QZ_STUCK_OCC (environment, read once): 16 | 20 | 24 resident warps per SM for the stuck pass -- an A/B knob; the default
+// is the measured best (see profiles/).
+#ifndef QZ_STUCK_OCC_DEFAULT
+#define QZ_STUCK_OCC_DEFAULT 16
+#endif
+static int qz_launch_stuck(const QzRolloutArgs &a, cudaStream_t st, const char *what) {
+    static const int occ = [] { const char *e = getenv("QZ_STUCK_OCC"); return e ? atoi(e) : QZ_STUCK_OCC_DEFAULT; }();
+    const int per_block = QZ_STUCK_THREADS / 32;
+    if (occ >= 24)
+        qz_rollout_stuck_kernel<24><<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel<24>, a.n_rollouts, per_block, QZ_STUCK_THREADS), QZ_STUCK_THREADS, 0, st>>>(a);
+    else if (occ >= 20)
+        qz_rollout_stuck_kernel<20><<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel<20>, a.n_rollouts, per_block, QZ_STUCK_THREADS), QZ_STUCK_THREADS, 0, st>>>(a);
+    else
+        qz_rollout_stuck_kernel<16><<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel<16>, a.n_rollouts, per_block, QZ_STUCK_THREADS), QZ_STUCK_THREADS, 0, st>>>(a);
+    return qz_check_launch(what);
+}
+
 static int qz_rollout_args(QzRolloutArgs &a, const qz_state *states, int64_t n_states, const int32_t *state_index,
                            int32_t per_state, int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids,
                            int32_t limit, int8_t *result, int32_t *plies, qz_state *final_states, void *workspace,
@@ -572,9 +594,7 @@ extern "C" int qz_rollout(const qz_state *states, int64_t n_states, const int32_
     if (rc) return rc;
     if (!(flags & QZ_ROLLOUT_DEFER_STUCK)) {
         // the number of ejected rollouts is only known on the device: launch a resident grid, blocks exit when the list is empty
-        qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, QZ_STUCK_THREADS / 32, QZ_STUCK_THREADS),
-                                  QZ_STUCK_THREADS, 0, st>>>(a);
-        rc = qz_check_launch("qz_rollout (stuck phase)");
+        rc = qz_launch_stuck(a, st, "qz_rollout (stuck phase)");
         if (rc) return rc;
     }
     return qz_pawn_passes(a, false, st, "qz_rollout (pawn phase)");
@@ -592,9 +612,7 @@ extern "C" int qz_rollout_finish(const qz_state *states, int64_t n_states, const
     cudaError_t e = cudaMemsetAsync(a.counter + 4, 0, 8, st);
     if (e == cudaSuccess) e = cudaMemsetAsync(a.counter + 8, 0, (QZ_WS_COUNTERS - 8) * 8, st);
     if (e != cudaSuccess) return qz_fail((int)e, "qz_rollout_finish: memset: %s", cudaGetErrorString(e));
-    qz_rollout_stuck_kernel<<<qz_persistent_blocks((const void *)qz_rollout_stuck_kernel, n_rollouts, QZ_STUCK_THREADS / 32, QZ_STUCK_THREADS),
-                                  QZ_STUCK_THREADS, 0, st>>>(a);
-    rc = qz_check_launch("qz_rollout_finish (stuck phase)");
+    rc = qz_launch_stuck(a, st, "qz_rollout_finish (stuck phase)");
     if (rc) return rc;
     return qz_pawn_passes(a, true, st, "qz_rollout_finish (pawn phase)");
 }
