@@ -495,33 +495,42 @@ static int qz_persistent_blocks(const void *kernel, int64_t n_items, int items_p
     return (int)(blocks < needed ? blocks : needed);
 }
 
-// The pawn phase as a sequence of passes.  A rollout plays at most `slice` plies per pass and is then parked; the next
+// The pawn phase as a sequence of passes.  A rollout plays at most slices[j] plies in pass j and is then parked; the next
 // pass picks the survivors up from a list, so they sit in full warps again instead of keeping a few lanes of
 // every warp alive for up to `limit` iterations (rollout lengths are heavy-tailed: mean ~300 plies, cap 1000).
 // The number of survivors is only known on the device: every pass launches a resident grid whose blocks exit at
 // once when there is nothing to claim.  `finish` = the deferred pass over stuck_list.
-static int64_t qz_pawn_slice(int64_t limit, int *passes) {
-    const int64_t span = limit > 1 ? limit - 1 : 1;                     // a rollout never plays more plies than this
-    int64_t slice = QZ_PAWN_SLICE;
-    if ((span + slice - 1) / slice > QZ_PAWN_MAX_PASSES) slice = (span + QZ_PAWN_MAX_PASSES - 1) / QZ_PAWN_MAX_PASSES;
-    *passes = (int)((span + slice - 1) / slice);
-    return slice;
+// Slice schedule: three slices of QZ_PAWN_SLICE plies, where re-packing the survivors pays (most rollouts end there), then
+// one of twice that, then whatever is left in a single pass -- the late passes hold a few per cent of the rollouts and
+// are bound by the latency of one ply, so every further launch only added its ramp (profiles/inst_table_summary.txt:
+// passes 4-8 of the uniform schedule ran at 11-20 % of the issue rate).  Returns the number of passes; slices[j] = plies
+// a rollout may play in pass j.
+static int qz_pawn_schedule(int64_t limit, int32_t *slices) {
+    int64_t left = limit > 1 ? limit - 1 : 1;                           // a rollout never plays more plies than this
+    int n = 0;
+    const int64_t plan[4] = {QZ_PAWN_SLICE, QZ_PAWN_SLICE, QZ_PAWN_SLICE, 2 * QZ_PAWN_SLICE};
+    while (left > 0 && n < 4) {
+        const int64_t sl = plan[n] < left ? plan[n] : left;
+        slices[n++] = (int32_t)sl;
+        left -= sl;
+    }
+    if (left > 0) slices[n++] = (int32_t)(left < 0x7FFFFFFF ? left : 0x7FFFFFFF);
+    return n;
 }
 
 extern "C" int32_t qz_rollout_pawn_passes(int32_t limit) {
-    int passes = 0;
-    qz_pawn_slice(limit, &passes);
-    return passes;
+    int32_t slices[8];
+    return qz_pawn_schedule(limit, slices);
 }
 
 static int qz_pawn_passes(QzRolloutArgs a, bool finish, cudaStream_t st, const char *what) {
-    int passes = 0;
-    const int64_t slice = qz_pawn_slice(a.limit, &passes);
+    int32_t slices[8];
+    const int passes = qz_pawn_schedule(a.limit, slices);
     int32_t *lists[2] = {a.stuck_list + qz_list_bytes(a.n_rollouts) / 4, a.stuck_list + 2 * (qz_list_bytes(a.n_rollouts) / 4)};
     int blocks = qz_persistent_blocks((const void *)qz_rollout_pawn_kernel, a.n_rollouts, QZ_PAWN_THREADS);
     if (finish) blocks = blocks / 4 > 0 ? blocks / 4 : 1;              // the deferred list is well under 1 % of the rollouts
-    a.slice = (int32_t)slice;
     for (int j = 0; j < passes; j++) {
+        a.slice = slices[j];
         a.work = a.counter + 8 + 2 * j;
         a.count_out = a.counter + 9 + 2 * j;
         a.list_out = lists[j & 1];

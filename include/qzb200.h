@@ -166,7 +166,7 @@ int qz_env_encode(const qz_state *states, void *out, int dtype, int layout, int 
 #define QZ_ROLLOUT_PENDING (-128)
 int64_t qz_rollout_workspace_bytes(int64_t n_rollouts);
 /* kernel launches of the pawn phase of one qz_rollout / qz_rollout_finish call (a rollout plays a bounded slice
- * of plies per pass, then the survivors are re-packed into full warps) */
+ * of plies per pass -- 128, 128, 128, 256, then the rest -- and the survivors are re-packed into full warps in between) */
 int32_t qz_rollout_pawn_passes(int32_t limit);
 int qz_rollout(const qz_state *states, int64_t n_states, const int32_t *state_index, int32_t per_state,
                int64_t n_rollouts, uint64_t seed, uint64_t rid_base, const uint64_t *rids, int32_t limit,
