@@ -34,7 +34,7 @@ SIGNATURES = {
     "qz_env_reset": (C.c_int, [_vp, _i64, _vp]),
     "qz_env_step": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _vp]),
     "qz_env_legal_mask": (C.c_int, [_vp, _vp, _i64, _vp]),
-    "qz_env_legal_mask_flagged": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _vp]),
+    "qz_env_legal_mask_flagged": (C.c_int, [_vp, _vp, C.c_int, _vp, _i64, _vp, _i32, C.c_int, _vp]),
     "qz_env_encode": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, _i64, _vp]),
     "qz_env_sample_legal": (C.c_int, [_vp, _vp, _u64, _vp, _vp, _i64, _vp]),
     "qz_env_random_play": (C.c_int, [_vp, _u64, _vp, _i32, _i64, _vp]),

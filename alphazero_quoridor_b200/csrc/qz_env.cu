@@ -78,12 +78,25 @@ __global__ void __launch_bounds__(128, 4) qz_legal_mask_kernel(const qz_state *_
 // The same sweep for the flagged positions only (lazy expansion, qz_mcts_extend: the leaves whose descent stopped at a
 // node that needs its legal set now); the masks of the others are left untouched.
 __global__ void __launch_bounds__(128, 4) qz_legal_mask_flagged_kernel(const qz_state *__restrict__ states,
-                                                                    const uint8_t *__restrict__ flags, int flag_bits,
-                                                                    uint64_t *__restrict__ mask3, int64_t n) {
+                                                                    uint8_t *__restrict__ flags, int flag_bits,
+                                                                    uint64_t *__restrict__ mask3, int64_t n,
+                                                                    const int32_t *__restrict__ key, int group, int dup_bits) {
     __shared__ uint32_t scratch[4][QZ_WARP_SCRATCH_WORDS];
     const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (g >= n) return;
     if (!(flags[g] & flag_bits)) return;
+    if (key != nullptr && group > 1) {
+        // an EARLIER flagged position of the same group with the same key (the leaves of one game that stopped at the
+        // same tree node) gets the sweep; this one is marked with dup_bits and skipped
+        const int64_t first = g - g % group;
+        const int32_t mine = key[g];
+        bool dup = false;
+        for (int64_t j = first + (threadIdx.x & 31); j < g; j += 32) dup |= (flags[j] & flag_bits) && key[j] == mine;
+        if (__any_sync(0xFFFFFFFFu, dup)) {
+            if ((threadIdx.x & 31) == 0) flags[g] |= (uint8_t)dup_bits;
+            return;
+        }
+    }
     const QzState s = qz_load_state(states + g);
     uint32_t pawn; uint64_t hl, vl;
     qz_warp_legal(s, pawn, hl, vl, scratch[threadIdx.x >> 5]);
@@ -95,8 +108,8 @@ __global__ void __launch_bounds__(128, 4) qz_legal_mask_flagged_kernel(const qz_
     }
 }
 
-extern "C" int qz_env_legal_mask_flagged(const qz_state *states, const uint8_t *flags, int flag_bits, uint64_t *mask3,
-                                         int64_t n, void *stream) {
+extern "C" int qz_env_legal_mask_flagged(const qz_state *states, uint8_t *flags, int flag_bits, uint64_t *mask3,
+                                         int64_t n, const int32_t *key, int32_t group, int dup_bits, void *stream) {
     QZ_REQUIRE(n >= 0);
     if (n == 0) return 0;
     QZ_REQUIRE_PTR(states);
@@ -104,7 +117,10 @@ extern "C" int qz_env_legal_mask_flagged(const qz_state *states, const uint8_t *
     QZ_REQUIRE_PTR(mask3);
     QZ_REQUIRE_ALIGN(states, 8);
     QZ_REQUIRE_ALIGN(mask3, 8);
-    qz_legal_mask_flagged_kernel<<<qz_blocks_for(n, 4), 128, 0, (cudaStream_t)stream>>>(states, flags, flag_bits, mask3, n);
+    QZ_REQUIRE(group >= 0);
+    QZ_REQUIRE((dup_bits & flag_bits) == 0);
+    qz_legal_mask_flagged_kernel<<<qz_blocks_for(n, 4), 128, 0, (cudaStream_t)stream>>>(states, flags, flag_bits, mask3, n, key,
+                                                                                       group, dup_bits);
     return qz_check_launch("qz_env_legal_mask_flagged");
 }
 

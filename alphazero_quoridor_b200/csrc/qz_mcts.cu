@@ -246,7 +246,24 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
                 if (UNIFORM_PRIOR && lazy_expand && b == QZ_CB_LAZY && !qz_done(s.meta)) flags |= QZ_LEAF_NEEDS_MASK;
                 break;
             }
-            const int m = at_root ? rm : visits[b], total = at_root ? rtotal : visits[b + 2];
+            // below the root only the block index is known at this point: the header, the legal mask and the first 32
+            // child slots are requested in ONE round of loads (slots past m hold garbage that is masked below) -- the
+            // descent is a chain of dependent loads, and this takes two links per level out of it
+            int hm = 0, hcap = 0, htot = 0;
+            double hq0 = 0.0, hq1 = 0.0, hq2 = 0.0, pq = 0.0;
+            uint32_t pcm = 0;
+            int pn = 0;
+            float pp = 0.0f;
+            if (!at_root) {
+                hm = visits[b]; hcap = visits[b + 1]; htot = visits[b + 2];
+                hq0 = q[b]; hq1 = q[b + 1]; hq2 = q[b + 2];
+                const int c0 = b + QZ_HDR + lane;
+                if (c0 < t.node_cap) {
+                    pcm = meta[c0]; pn = visits[c0]; pq = q[c0];
+                    if (!UNIFORM_PRIOR) pp = prior[c0];
+                }
+            }
+            const int m = at_root ? rm : hm, total = at_root ? rtotal : htot;
             const uint32_t pm = at_root ? rmeta + ((uint32_t)root_marks << 16) : meta[node];
             const int np_eff = (at_root ? rvis : visits[node]) + qz_meta_inflight(pm) - 1;  // minus this descent's own mark
             const double sq = sqrt((double)np_eff);                     // np.sqrt(parent._n_visits)
@@ -263,9 +280,10 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
             } else
             for (int j = lane; j < m; j += 32) {
                 const int c = b + QZ_HDR + j;
-                const uint32_t cm = at_root ? s_meta[wib][j] : meta[c];
-                const int n = at_root ? s_n[wib][j] : visits[c], infl = qz_meta_inflight(cm);
-                double qv = at_root ? s_q[wib][j] : q[c];
+                const bool pre = !at_root && j == lane;                 // first round below the root: loaded above
+                const uint32_t cm = at_root ? s_meta[wib][j] : (pre ? pcm : meta[c]);
+                const int n = at_root ? s_n[wib][j] : (pre ? pn : visits[c]), infl = qz_meta_inflight(cm);
+                double qv = at_root ? s_q[wib][j] : (pre ? pq : q[c]);
                 if (infl > 0) {                                         // virtual loss (K > 1 only)
                     // a zero numerator (e.g. one win, one mark) would send the FP64 division down its ~100-instruction
                     // special-case path, which was a quarter of this kernel's instructions; 0 / x is +0 either way
@@ -274,7 +292,7 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
                 }
                 double cp;
                 if (UNIFORM_PRIOR) cp = uni;
-                else cp = (double)(c_puct_f * (at_root ? s_prior[wib][j] : prior[c]));   // float32 product first (numpy weak scalar)
+                else cp = (double)(c_puct_f * (at_root ? s_prior[wib][j] : (pre ? pp : prior[c])));   // float32 product first (numpy weak scalar)
                 const double u = cp * sq / (double)(1 + n + infl);      // mcts.py:69
                 const double val = qv + u;
                 const int rank = qz_meta_rank(cm);
@@ -292,7 +310,13 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
             float uprior = 0.0f;
             uint32_t pawn = 0; uint64_t hl = 0, vl = 0;
             if (m < total) {
-                qz_header_mask(v, b, pawn, hl, vl);
+                if (at_root) {
+                    qz_header_mask(v, b, pawn, hl, vl);
+                } else {
+                    const uint64_t mk[3] = {(uint64_t)__double_as_longlong(hq0), (uint64_t)__double_as_longlong(hq1),
+                                            (uint64_t)__double_as_longlong(hq2)};
+                    qz_unpack_mask(mk, pawn, hl, vl);
+                }
                 double cpu;
                 if (UNIFORM_PRIOR) {
                     cpu = uni; urank = m;                                // slots are made in actions() order
@@ -306,7 +330,7 @@ __global__ void __launch_bounds__(128, 6) qz_mcts_select_kernel(qz_tree t, doubl
             if (take_new) {
                 uact = qz_action_of_rank(pawn, hl, vl, urank);
                 if (UNIFORM_PRIOR) uprior = 1.0f / (float)total;
-                int cap = visits[b + 1];
+                int cap = at_root ? visits[b + 1] : hcap;
                 bool room = true;
                 if (m == cap) {
                     // the block is full: move it to one of twice the size; the old slots forward to the new ones
@@ -450,6 +474,8 @@ __global__ void __launch_bounds__(128, 4) qz_mcts_extend_kernel(qz_tree t, doubl
         if (!(flags & QZ_LEAF_NEEDS_MASK)) continue;
         flags &= ~QZ_LEAF_NEEDS_MASK;
         touched = true;
+        const bool swept = !(flags & QZ_LEAF_DUPLICATE);               // its mask3 row was computed (see the flagged sweep)
+        flags &= ~QZ_LEAF_DUPLICATE;
         const int X = qz_resolve(child_base, t.leaf_node[L]);
         QzState s = qz_load_state(t.leaf_state + L);
         const int len = t.path_len[L];
@@ -457,7 +483,9 @@ __global__ void __launch_bounds__(128, 4) qz_mcts_extend_kernel(qz_tree t, doubl
         uint32_t pawn; uint64_t hl, vl;
         __syncwarp();
         if (b < 0) {                                                    // first descent to come back to X: expand it now
-            if (mask3 != nullptr) {                                     // swept in parallel by qz_env_legal_mask_flagged
+            // swept in parallel by qz_env_legal_mask_flagged -- unless this leaf was skipped there as the duplicate of an
+            // earlier one whose node then could NOT be given a block (no legal action, arena full): swept here
+            if (mask3 != nullptr && swept) {
                 const uint64_t mk[3] = {mask3[3 * L], mask3[3 * L + 1], mask3[3 * L + 2]};
                 qz_unpack_mask(mk, pawn, hl, vl);
             } else {

@@ -242,6 +242,7 @@ class BatchedMCTS:
         self.total_playouts = 0
         self.count_tree_steps = False    # bench: accumulate the env steps replayed by the descents
         self.tree_steps = torch.zeros((), dtype=torch.int64, device=dev)
+        self._count_sets = []
         self._structs = [[self._make_struct(a, ls) for ls in self.sets] for a in self.arenas]
 
     # ---- plumbing ----
@@ -368,6 +369,11 @@ class BatchedMCTS:
                         self._launch_finish(idx)
                 for idx in order:
                     self._settle(idx)
+        if self._count_sets:
+            # descent steps of every wave since the last drain in ONE reduction (no per-wave torch kernels)
+            lens = torch.stack([ls.path_len for ls in self._count_sets])
+            self.tree_steps += (lens.clamp(min=1) - 1).sum()
+            self._count_sets = []
 
     def playout_wave(self, k_leaves=None):
         """One wave: k_leaves playouts per game (mcts.py:103-127)."""
@@ -387,7 +393,8 @@ class BatchedMCTS:
                 # uniform priors: a leaf's legal actions are only computed when a later playout comes back to it -- swept
                 # for the flagged leaves in parallel (a warp per leaf), then the block is built and the descent continued
                 _lib.check(self.lib.qz_env_legal_mask_flagged(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_flags),
-                                                              LEAF_NEEDS_MASK, _lib.ptr(ls.leaf_mask), m, st),
+                                                              LEAF_NEEDS_MASK, _lib.ptr(ls.leaf_mask), m,
+                                                              _lib.ptr(ls.leaf_node), self.K, LEAF_DUPLICATE, st),
                            "qz_env_legal_mask_flagged")
                 _lib.check(self.lib.qz_mcts_extend(C.byref(self.tree), self.c_puct, _lib.ptr(ls.leaf_mask), 0,
                                                    _lib.ptr(self.overflow), st), "qz_mcts_extend")
@@ -395,7 +402,10 @@ class BatchedMCTS:
                 _lib.check(self.lib.qz_env_legal_mask(_lib.ptr(ls.leaf_state), _lib.ptr(ls.leaf_mask), m, st),
                            "qz_env_legal_mask")
             if self.count_tree_steps:
-                self.tree_steps += (ls.path_len.clamp(min=1) - 1).sum()
+                if self.defer_until_drain:
+                    self._count_sets.append(ls)     # one leaf set per wave: summed once, when the search drains
+                else:
+                    self.tree_steps += (ls.path_len.clamp(min=1) - 1).sum()
             # rollout / RNG stream of leaf (g,k): (game id, playout counter) in separate bit fields, so two games can
             # never share a stream (pure_mcts.py:86-108 draws fresh randomness for every rollout)
             rids = None

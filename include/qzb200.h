@@ -106,9 +106,12 @@ int qz_env_step(qz_state *states, const int32_t *actions, const uint64_t *legal_
 int qz_env_legal_mask(const qz_state *states, uint64_t *mask3, int64_t n, void *stream);
 
 /* The same for the positions whose flags[i] & flag_bits != 0 only (the others' masks are left untouched): the lazily
- * expanded search sweeps just the leaves that came back to a node (flags = qz_tree.leaf_flags, QZ_LEAF_NEEDS_MASK). */
-int qz_env_legal_mask_flagged(const qz_state *states, const uint8_t *flags, int flag_bits, uint64_t *mask3, int64_t n,
-                              void *stream);
+ * expanded search sweeps just the leaves that came back to a node (flags = qz_tree.leaf_flags, QZ_LEAF_NEEDS_MASK).
+ * key / group (nullable / 0): positions are grouped in runs of `group` (the leaves of one game); a flagged position whose
+ * key equals that of an earlier flagged position of its group (the same tree node, key = qz_tree.leaf_node) is not swept
+ * but marked with dup_bits in flags (qz_mcts_extend builds a node's block from the first of them; QZ_LEAF_DUPLICATE). */
+int qz_env_legal_mask_flagged(const qz_state *states, uint8_t *flags, int flag_bits, uint64_t *mask3, int64_t n,
+                              const int32_t *key, int32_t group, int dup_bits, void *stream);
 
 /*
  * The reference's random policy over the FULL legal set (pure_mcts.rollout_policy_fn, pure_mcts.py:7-10: argmax of
