@@ -42,6 +42,24 @@ for ev, K, reuse, defer in ((tree.StubEvaluator("S3"), 1, True, 0), (tree.StubEv
         mv = eng.choose(mode=mode, temp=1.0, seed=3)
     eng.advance(mv, keep_subtree=reuse)
     eng.search(8)
+# round 2: lazy child slots with block growth + forwarding, lazy expansion (flagged sweep + extend), end-of-search stuck
+# passes, a one-playout search (root block built at the end), the node view, re-rooting with the prior pool
+eng = tree.BatchedMCTS(n, tree.RolloutEvaluator(seed=2), c_puct=5, n_playout=160, leaves_per_game=8, reuse_tree=False,
+                       defer_until_drain=True)
+eng.reset(st)
+eng.search()
+eng.choose(mode=0)
+eng.node_children(0, 0)
+one = tree.BatchedMCTS(n, tree.RolloutEvaluator(seed=3), c_puct=5, n_playout=1, leaves_per_game=1, reuse_tree=False)
+one.reset(st)
+one.search()
+one.root_stats(temp=1.0)
+deep = tree.BatchedMCTS(16, tree.StubEvaluator("S2"), c_puct=5, n_playout=300, leaves_per_game=1, reuse_tree=True)
+deep.reset(late[sel][:16].contiguous())
+for _ in range(3):
+    deep.search()
+    deep.advance(deep.choose(mode=0), keep_subtree=True)
+deep.check_device()
 sp = BatchedSelfPlay(64, tree.StubEvaluator("S3"), n_playout=16, leaves_per_game=2, record=True, fix_terminal_sign=True,
                      max_plies=60)
 for _ in range(12):
