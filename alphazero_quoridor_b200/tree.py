@@ -1,7 +1,9 @@
 """Batched PUCT MCTS on the GPU: the engine behind `mcts.MCTS` / `pure_mcts.MCTS` (mcts.py, pure_mcts.py).
 
-`BatchedMCTS` owns the flat tree arrays (torch CUDA tensors) of n concurrent games and drives the
-select -> legal-mask -> evaluate -> expand+backup kernels of libqzb200.so.  Evaluators:
+`BatchedMCTS` owns the flat tree arrays (torch CUDA tensors) of n concurrent games and drives the kernels of
+libqzb200.so, one wave = select -> legal masks -> evaluate -> expand + backup (stored priors), or
+select -> sweep of the revisited leaves -> extend -> rollouts -> backup (uniform priors, lazy expansion).  A child gets
+its slot in the arrays the first time the descent picks it (csrc/qz_mcts.cu).  Evaluators:
 
 * `StubEvaluator(kind)`     deterministic parity stubs S1/S2/S3 (tests/golden/stubs.py), on the device
 * `RolloutEvaluator(seed)`  pure MCTS: uniform priors + random rollout (pure_mcts.py:13-16,86-108)
