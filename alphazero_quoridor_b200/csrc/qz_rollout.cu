@@ -76,11 +76,18 @@ __device__ __forceinline__ int64_t qz_start_index(const QzRolloutArgs &a, int64_
 #define QZ_MAX_REJECTS 2u
 #endif
 
+// The unit of work of one loop iteration is ONE DRAW ATTEMPT per lane (qz_sample.cuh), not one ply: a lane whose drawn
+// wall failed the path check retries in the next iteration while its neighbours, whose draws were accepted, already play
+// their next ply.  With a ply as the unit, a warp waited for its slowest lane -- and with 32 lanes some lane redraws on
+// four plies out of five (profiles/r2j_wave_ncu_full.txt: 16 active lanes per instruction).  The attempt sequence, the
+// "already known to block" sets and the ejection rule are exactly those of qz_sample_action_capped.
 __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a) {
     QzState s;
     QzRng rng;
     int64_t r = -1;
     int steps = 0;
+    uint32_t j = 0, n_bad = 0;                                          // attempt of the current ply, walls found to block
+    uint64_t bad_h = 0, bad_v = 0;
     bool exhausted = false;
     s.H = s.V = s.meta = 0;
     rng = qz_rng_init(0, 0);
@@ -93,6 +100,7 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
                 s = qz_load_state(a.states + qz_start_index(a, r));
                 rng = qz_rng_init(a.seed, a.rids ? __ldg(a.rids + r) : a.rid_base + (uint64_t)r);
                 steps = 0;
+                j = 0; n_bad = 0; bad_h = bad_v = 0;
             } else {
                 exhausted = true;
             }
@@ -101,18 +109,50 @@ __global__ void __launch_bounds__(128, 4) qz_rollout_wall_kernel(QzRolloutArgs a
         if (r >= 0) {
             bool leave = qz_done(s.meta) || steps >= a.limit - 1 || (qz_w1(s.meta) + qz_w2(s.meta)) == 0;
             if (!leave) {
-                const int act = qz_sample_action_capped(s, rng, (uint32_t)steps, QZ_MAX_REJECTS);
-                if (act == -2) {                                        // stuck: hand over to qz_rollout_stuck_kernel
+                const QzPawnCtx c = qz_ctx_build(s.H, s.V);
+                const uint32_t pmask = qz_mover_pawn_moves_ctx(c, s.meta);
+                uint64_t hc = 0, vc = 0;
+                if (qz_mover_walls(s.meta) > 0) { hc = qz_hcand(s.H, s.V); vc = qz_vcand(s.H, s.V); }
+                const int npawn = qz_popc32(pmask), nh = qz_popc64(hc), nv = qz_popc64(vc);
+                const uint32_t M = (uint32_t)(npawn + nh + nv);
+                bool accept = false, stale = M == 0, eject = false;
+                int act = -1;
+                if (!stale) {
+                    const uint32_t word = qz_attempt_word(rng, (uint32_t)steps, j);
+                    act = qz_superset_action(pmask, hc, vc, npawn, nh, (int)qz_mulhi32(word, M));
+                    if (act < 12) {
+                        accept = true;                                  // a pawn move of the superset is legal as it stands
+                    } else {
+                        const bool vert = act >= 76;
+                        const int ix = vert ? act - 76 : act - 12;
+                        const uint64_t bit = 1ull << ix;
+                        if (!((vert ? bad_v : bad_h) & bit)) {          // (drawn again: still illegal, next attempt)
+                            const QzSweep w = qz_sweep_prepare_ctx(c, s.H, s.V, qz_p1(s.meta), qz_p2(s.meta));
+                            if (qz_wall_keeps_paths(w, ix, vert)) {
+                                accept = true;
+                            } else {
+                                if (vert) bad_v |= bit; else bad_h |= bit;
+                                n_bad++;
+                                if (npawn == 0 && n_bad == M) stale = true;            // every candidate is a blocking wall
+                                else if (n_bad > QZ_MAX_REJECTS) eject = true;
+                            }
+                        }
+                    }
+                }
+                if (accept) {
+                    s = qz_apply(s, act);
+                    steps++;
+                    j = 0; n_bad = 0; bad_h = bad_v = 0;
+                } else if (eject) {                                     // stuck: hand over to qz_rollout_stuck_kernel
                     const unsigned long long k = atomicAdd(a.counter + 3, 1ull);
                     a.stuck_list[k] = (int32_t)r;
                     s.meta |= (uint64_t)QZ_FLAG_PENDING << 40;
                     leave = true;
-                } else if (act < 0) {
+                } else if (stale) {
                     s.meta |= (uint64_t)QZ_FLAG_STALEMATE << 40;
                     leave = true;
                 } else {
-                    s = qz_apply(s, act);
-                    steps++;
+                    j++;
                 }
             }
             if (leave) {
