@@ -189,3 +189,29 @@ def test_replay_ring_matches_deque():
             vals = s[:, 0].tolist()
             assert len(set(vals)) == 10 and set(vals) <= set(dq)
     assert rb[0][0][0].item() == dq[0] and rb[0][2] == 1.0
+
+
+def test_mirror_samples_is_an_involution_on_cpu():
+    """train.mirror_samples (left-right symmetry of states and the 140 move probabilities) is plain tensor arithmetic:
+    applying it twice is the identity, the action permutation is a bijection that maps wall (r, c) to (r, 7 - c), and
+    z is untouched.  (The GPU suite checks it against the kernels' planes and legal lists.)"""
+    from alphazero_quoridor_b200.train import MIRROR_ACTION, mirror_samples
+    g = torch.Generator().manual_seed(1)
+    n = 64
+    H = torch.randint(0, 2 ** 62, (n,), generator=g, dtype=torch.int64)
+    V = torch.randint(0, 2 ** 62, (n,), generator=g, dtype=torch.int64) & ~H
+    p1 = torch.randint(0, 81, (n,), generator=g)
+    p2 = torch.randint(0, 81, (n,), generator=g)
+    meta = p1 | (p2 << 8) | (torch.randint(0, 11, (n,), generator=g) << 16) | (torch.randint(0, 11, (n,), generator=g) << 24) \
+        | (torch.randint(1, 3, (n,), generator=g) << 32) | (torch.randint(0, 200, (n,), generator=g) << 48)
+    st = torch.stack([H, V, meta], 1)
+    pr = torch.rand((n, 140), generator=g)
+    m_st, m_pr = mirror_samples(st, pr)
+    b_st, b_pr = mirror_samples(m_st, m_pr)
+    assert torch.equal(b_st, st) and torch.equal(b_pr, pr)
+    assert sorted(MIRROR_ACTION.tolist()) == list(range(140))
+    assert MIRROR_ACTION[12 + 8 * 3 + 1].item() == 12 + 8 * 3 + 6 and MIRROR_ACTION[76 + 8 * 5 + 0].item() == 76 + 8 * 5 + 7
+    assert MIRROR_ACTION[2].item() == 3 and MIRROR_ACTION[8].item() == 9           # E <-> W, NE <-> NW
+    assert torch.equal((m_st[:, 2] >> 16), (st[:, 2] >> 16))                        # walls left, mover, flags, ply untouched
+    assert torch.equal((m_st[:, 2] & 0xFF) % 9, 8 - (st[:, 2] & 0xFF) % 9)          # pawn columns mirrored
+    assert torch.equal((m_st[:, 2] & 0xFF) // 9, (st[:, 2] & 0xFF) // 9)            # rows kept
