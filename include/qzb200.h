@@ -239,7 +239,10 @@ int qz_mcts_init(const qz_tree *tree, const qz_state *root_states, const uint8_t
  * get_value, mcts.py:37-42,64-70), replaying Quoridor.step from root_state.  Fills the per-leaf arrays.
  * uniform_prior != 0: priors are 1/len(children) in float64 (pure_mcts.py:13-16) instead of the stored f32.
  * With k_leaves > 1 later descents see a virtual loss on earlier paths (deviation; k_leaves = 1 is exact).
- * A child picked for the first time gets its slot here (overflow_count, nullable, counts the slots that did not fit). */
+ * A child picked for the first time gets its slot here (overflow_count, nullable, counts the slots that did not fit).
+ * lazy_expand != 0 (uniform priors only): see qz_mcts_extend below.  With leaves_per_game > 1 the root's per-child terms
+ * are kept as reciprocals in shared memory (one fused multiply-add per child instead of two float64 divisions); the
+ * one-leaf-per-wave search keeps the reference's literal arithmetic. */
 int qz_mcts_select(const qz_tree *tree, double c_puct, int uniform_prior, int k_leaves, int lazy_expand,
                    int32_t *overflow_count, void *stream);
 
