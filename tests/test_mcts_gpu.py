@@ -434,3 +434,62 @@ def test_full_size_configs_properties(qz):
         outs.append((v.clone(), mv.clone()))
         assert (v[0].nonzero().flatten().cpu().tolist() == sorted(qz.q.Quoridor().actions()))     # all 131 root moves tried
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
+def test_lazy_expansion_equals_eager(qz):
+    """Lazy expansion (a node's legal set computed when a playout comes back to it, qz_mcts_extend) against expansion at
+    the first visit (the reference's order, pure_mcts.py:75-79): the same trees, visit for visit, at K = 1 and at K = 8
+    (no deferral), with real rollouts on the same streams."""
+    n = 96
+    states = _positions(n, seed=41, min_plies=0, max_plies=40)
+    for K, npl in ((1, 70), (8, 200)):
+        out = []
+        for lazy in (True, False):
+            eng = qz.tree.BatchedMCTS(n, qz.tree.RolloutEvaluator(seed=5), c_puct=5, n_playout=npl, leaves_per_game=K,
+                                      reuse_tree=False, lazy_expand=lazy)
+            assert eng.lazy_expand == lazy
+            eng.reset(states)
+            eng.search()
+            v, _, rn, q = eng.root_stats(temp=1.0, want_q=True)
+            assert (rn == npl).all() and eng.overflow_count() == 0
+            out.append((v.cpu(), q.cpu(), eng.choose(mode=0).cpu()))
+        assert torch.equal(out[0][0], out[1][0]), K
+        assert torch.equal(out[0][1], out[1][1]) and torch.equal(out[0][2], out[1][2])
+
+
+def test_node_view_lists_unvisited_children(qz):
+    """`node_children` / the TreeNode view show every legal action in actions() order -- children that never got a slot
+    included (0 visits, Q 0, their prior), as the reference's freshly expanded children (mcts.py:27-35)."""
+    st = _positions(4, seed=3, min_plies=6, max_plies=12)
+    eng = qz.tree.BatchedMCTS(4, qz.tree.StubEvaluator("S2"), c_puct=5, n_playout=30, leaves_per_game=1, reuse_tree=True)
+    eng.reset(st)
+    eng.search()
+    legal = qz.q.BatchedQuoridor(4, states=st.clone()).legal_lists()
+    visits, _, _ = eng.root_stats(temp=1.0)
+    for g in range(4):
+        kids, me = eng.node_children(g, int(eng.arena.root[g].item()))
+        assert [k["action"] for k in kids] == legal[g] and me["visits"] == 30
+        assert sum(k["visits"] for k in kids) == 29
+        assert sum(1 for k in kids if k["slot"] >= 0) <= 29 < len(kids)          # most children never got a slot
+        for k in kids:
+            assert k["visits"] == int(visits[g, k["action"]].item())
+            assert 0.0 < k["prior"] <= 2.0 ** -6 + 1e-12                          # S2 priors, present for unvisited ones too
+            if k["slot"] < 0:
+                assert k["visits"] == 0 and k["q"] == 0.0
+
+
+def test_arena_overflow_is_counted_not_fatal(qz):
+    """An arena that is too small costs exactness, never memory safety: playouts whose slot or block does not fit are
+    evaluated where they stand and counted (qz_tree sizing note in include/qzb200.h)."""
+    n = 32
+    st = _positions(n, seed=9, min_plies=0, max_plies=20)
+    for ev, kw in ((qz.tree.StubEvaluator("S3"), {}), (qz.tree.RolloutEvaluator(seed=2), dict(defer_until_drain=True))):
+        eng = qz.tree.BatchedMCTS(n, ev, c_puct=5, n_playout=300, leaves_per_game=4, reuse_tree=False, node_cap=400, **kw)
+        eng.reset(st)
+        eng.search()
+        v, _, rn = eng.root_stats(temp=1.0)
+        assert eng.overflow_count() > 0
+        assert (rn == 300).all() and (v.sum(1) <= 299).all() and (v >= 0).all()
+        mv = eng.choose(mode=0)
+        assert ((mv >= -1) & (mv < 140)).all()
+        eng.check_device()
